@@ -1,0 +1,244 @@
+"""Host-side mirror of the reference's `namespace gpu` interface for the pyramidal LK path.
+
+Function names, argument order and meaning follow OptFlowGpu.cuh (reference): `gauss_pyramid` (:21),
+`calc_opt_flow` (:33), `conv_3ch_1ch_tiled_uchar_float` (:17), `srm_1ch_float` (:25),
+`inverse_matrix_float` (:31).  Host images are numpy u8 arrays in the reference layout
+(h, w, 3 interleaved channels); flow is float32 (h, w, 2).  Everything computes on the GPU through
+the C ABI in include/ofb200.h -- there is no CPU path here.
+
+The device-resident entry points (`flow_pairs_device`, `lk_level_device`, `pyr_down_device`) take
+torch CUDA tensors only as owners of device memory; torch does none of the arithmetic.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+import numpy as np
+
+from . import _lib as L
+from ._lib import WARP_AS_WRITTEN, WARP_BILINEAR, WARP_NEAREST, OfbError, OfbParams  # noqa: F401
+
+REFERENCE_WINDOW = 19  # OptFlowGpu.cu:1944-1945
+
+
+def _u8(a: np.ndarray) -> np.ndarray:
+    if a.dtype != np.uint8 or not a.flags["C_CONTIGUOUS"]:
+        raise TypeError("expected a C-contiguous uint8 array")
+    return a
+
+
+def _f32(a: np.ndarray) -> np.ndarray:
+    if a.dtype != np.float32 or not a.flags["C_CONTIGUOUS"]:
+        raise TypeError("expected a C-contiguous float32 array")
+    return a
+
+
+def _ptrs(arrs: Sequence[np.ndarray], t):
+    return (t * len(arrs))(*[a.ctypes.data_as(t) for a in arrs])
+
+
+def align_up(v: int, a: int) -> int:
+    return (v + a - 1) // a * a
+
+
+class Context:
+    """One per GPU (ofb_ctx): owns the device workspace reused across calls."""
+
+    def __init__(self, device: int = 0):
+        self._lib = L.load()
+        h = C.c_void_p()
+        L.check(self._lib.ofb_ctx_create(int(device), C.byref(h)))
+        self._h = h
+        self.device = int(device)
+
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            self._lib.ofb_ctx_destroy(self._h)
+            self._h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def sm_count(self) -> int:
+        v = C.c_int()
+        L.check(self._lib.ofb_ctx_sm_count(self._h, C.byref(v)))
+        return v.value
+
+    @property
+    def launch_count(self) -> int:
+        v = C.c_ulonglong()
+        L.check(self._lib.ofb_ctx_launch_count(self._h, C.byref(v)))
+        return v.value
+
+    # ---------------------------------------------------------------- reference-named host API
+    def gauss_pyramid(self, pyramid: Sequence[np.ndarray], w: int, h: int, levels: int) -> None:
+        """gpu::gauss_pyramid (OptFlowGpu.cu:1262): fills pyramid[1..levels-1] from pyramid[0] in place.
+        pyramid[k] is a (h>>k, w>>k, 3) uint8 array."""
+        for k in range(levels):
+            if pyramid[k].shape != (h >> k, w >> k, 3):
+                raise ValueError(f"pyramid[{k}] has shape {pyramid[k].shape}, expected {(h >> k, w >> k, 3)}")
+        arrs = [_u8(p) for p in pyramid[:levels]]
+        L.check(self._lib.ofb_gauss_pyramid_host_u8c3(self._h, _ptrs(arrs, L.u8p), w, h, levels))
+
+    def calc_opt_flow(self, prev: np.ndarray, next: np.ndarray, w: int, h: int, optFlowPyramid: Sequence[np.ndarray],
+                      level: int, maxLevel: int, win: int = REFERENCE_WINDOW, warp_mode: int = WARP_AS_WRITTEN,
+                      flow_scale: float = 1.0) -> None:
+        """gpu::calc_opt_flow (OptFlowGpu.cu:1909): one level; reads optFlowPyramid[k > level], writes
+        optFlowPyramid[level] in place.  Defaults reproduce the reference (window 19, its warp as written)."""
+        if prev.shape != (h, w, 3) or next.shape != (h, w, 3):
+            raise ValueError("prev/next must be (h, w, 3) uint8")
+        arrs = [_f32(f) for f in optFlowPyramid[:maxLevel]]
+        for k in range(level, maxLevel):
+            exp = (h >> (k - level), w >> (k - level), 2)
+            if arrs[k].shape != exp:
+                raise ValueError(f"optFlowPyramid[{k}] has shape {arrs[k].shape}, expected {exp}")
+        ptrs = (L.f32p * maxLevel)(*[a.ctypes.data_as(L.f32p) for a in arrs])
+        L.check(self._lib.ofb_calc_opt_flow_host_u8c3(self._h, _u8(prev).ctypes.data_as(L.u8p),
+                                                      _u8(next).ctypes.data_as(L.u8p), w, h, ptrs, level, maxLevel, win,
+                                                      warp_mode, C.c_float(flow_scale)))
+
+    def conv_3ch_1ch_tiled_uchar_float(self, src: np.ndarray, w: int, h: int, mask: np.ndarray, mw: int, mh: int) -> np.ndarray:
+        """gpu::conv_3ch_1ch_tiled_uchar_float (OptFlowGpu.cu:1100)."""
+        if src.shape != (h, w, 3):
+            raise ValueError("src must be (h, w, 3) uint8")
+        mask = np.ascontiguousarray(mask, np.float32).reshape(-1)
+        if mask.size != mw * mh:
+            raise ValueError("mask size does not match mw*mh")
+        dst = np.empty((h, w), np.float32)
+        L.check(self._lib.ofb_conv_3ch_1ch_u8_f32_host(self._h, _u8(src).ctypes.data_as(L.u8p), w, h,
+                                                       dst.ctypes.data_as(L.f32p), mask.ctypes.data_as(L.f32p), mw, mh))
+        return dst
+
+    def srm_1ch_float(self, arr1: np.ndarray, arr2: np.ndarray, w: int, h: int, ww: int, wh: int) -> np.ndarray:
+        """gpu::srm_1ch_float (OptFlowGpu.cu:1597)."""
+        if arr1.shape != (h, w) or arr2.shape != (h, w):
+            raise ValueError("arr1/arr2 must be (h, w) float32")
+        dst = np.empty((h, w), np.float32)
+        L.check(self._lib.ofb_srm_1ch_f32_host(self._h, _f32(arr1).ctypes.data_as(L.f32p), _f32(arr2).ctypes.data_as(L.f32p),
+                                               w, h, ww, wh, dst.ctypes.data_as(L.f32p)))
+        return dst
+
+    def inverse_matrix_float(self, sumIx2, sumIy2, sumIxIy, sumIxIt, sumIyIt, optFlowPyramid: Sequence[np.ndarray],
+                             level: int, w: int, h: int) -> None:
+        """gpu::inverse_matrix_float (OptFlowGpu.cu:1858): writes optFlowPyramid[level] in place."""
+        sums = [_f32(s) for s in (sumIx2, sumIy2, sumIxIy, sumIxIt, sumIyIt)]
+        for s in sums:
+            if s.shape != (h, w):
+                raise ValueError("sums must be (h, w) float32")
+        arrs = [_f32(f) for f in optFlowPyramid[:level + 1]]
+        if arrs[level].shape != (h, w, 2):
+            raise ValueError("optFlowPyramid[level] must be (h, w, 2) float32")
+        ptrs = (L.f32p * (level + 1))(*[a.ctypes.data_as(L.f32p) for a in arrs])
+        L.check(self._lib.ofb_inverse_matrix_f32_host(self._h, *[s.ctypes.data_as(L.f32p) for s in sums], ptrs, level, w, h))
+
+    # ---------------------------------------------------------------- whole-pair host API
+    def flow_pairs_host(self, prev: np.ndarray, next: np.ndarray, levels: int, win: int,
+                        warp_mode: int = WARP_BILINEAR, flow_scale: float = 1.0,
+                        out: Optional[Sequence[np.ndarray]] = None) -> list[np.ndarray]:
+        """The loop of main.cu:246-262 for a batch with host buffers.  prev/next: (n, h, w) gray or
+        (n, h, w, 3) reference layout (a single pair may omit n).  Returns the residual flow of every
+        level, level 0 first, each (n, h>>k, w>>k, 2)."""
+        if prev.ndim == 4:
+            if prev.shape[3] != 3:
+                raise ValueError("4-d input must be (n, h, w, 3)")
+            channels = 3
+            n, h, w = prev.shape[0], prev.shape[1], prev.shape[2]
+        elif prev.ndim == 3:
+            channels = 1
+            n, h, w = prev.shape
+        elif prev.ndim == 2:
+            channels = 1
+            n, (h, w) = 1, prev.shape
+        else:
+            raise ValueError("prev must be (n,h,w), (h,w) or (n,h,w,3)")
+        if next.shape != prev.shape:
+            raise ValueError("prev and next differ in shape")
+        p = OfbParams(w, h, levels, win, warp_mode, flow_scale, n)
+        if out is None:
+            out = [np.empty((n, h >> k, w >> k, 2), np.float32) for k in range(levels)]
+        ptrs = (L.f32p * levels)(*[_f32(o).ctypes.data_as(L.f32p) for o in out])
+        L.check(self._lib.ofb_flow_pairs_host(self._h, C.byref(p), _u8(prev).ctypes.data_as(L.u8p),
+                                              _u8(next).ctypes.data_as(L.u8p), channels, ptrs))
+        return list(out)
+
+    # ---------------------------------------------------------------- device-resident API
+    def flow_pairs_device(self, prev, next, w: int, levels: int, win: int, warp_mode: int = WARP_BILINEAR,
+                          flow_scale: float = 1.0, flows=None, total_flow=None, stream: int = 0):
+        """prev/next: torch.uint8 CUDA tensors (n, h, pitch) with pitch % 16 == 0 and pitch >= w.
+        Returns the list of residual-flow tensors (n, h>>k, w>>k, 2); pass `flows` to reuse buffers."""
+        import torch
+
+        if prev.dtype != torch.uint8 or prev.dim() != 3 or not prev.is_contiguous() or prev.shape != next.shape:
+            raise ValueError("prev/next must be contiguous uint8 (n, h, pitch) CUDA tensors of equal shape")
+        n, h, pitch = prev.shape
+        if flows is None:
+            flows = [torch.empty((n, h >> k, w >> k, 2), dtype=torch.float32, device=prev.device) for k in range(levels)]
+        p = OfbParams(w, h, levels, win, warp_mode, flow_scale, n)
+        ptrs = (C.c_void_p * levels)(*[f.data_ptr() for f in flows])
+        L.check(self._lib.ofb_flow_pairs_device(self._h, C.byref(p), prev.data_ptr(), next.data_ptr(), pitch, pitch * h,
+                                                ptrs, total_flow.data_ptr() if total_flow is not None else None,
+                                                C.c_void_p(stream)))
+        return flows
+
+    def pyr_down_device(self, src, sw: int, dst=None, stream: int = 0):
+        """src: torch.uint8 (n, sh, pitch) -> dst (n, sh>>1, pitch_d)."""
+        import torch
+
+        n, sh, sp = src.shape
+        dw, dh = sw >> 1, sh >> 1
+        if dst is None:
+            dst = torch.zeros((n, dh, align_up(dw, 64)), dtype=torch.uint8, device=src.device)
+        dp = dst.shape[2]
+        L.check(self._lib.ofb_pyr_down_device(self._h, src.data_ptr(), sp, sp * sh, sw, sh, dst.data_ptr(), dp, dp * dh, n,
+                                              C.c_void_p(stream)))
+        return dst
+
+    def lk_level_device(self, prev, next, w: int, win: int, warp_mode: int = WARP_BILINEAR, flow_scale: float = 1.0,
+                        cum_in=None, flow_out=None, cum_out=None, stream: int = 0):
+        """One fused LK level on (n, h, pitch) uint8 tensors; cum_in is the (n, h>>1, w>>1, 2) cumulative
+        flow of the coarser level or None for the coarsest level."""
+        import torch
+
+        n, h, pitch = prev.shape
+        if flow_out is None:
+            flow_out = torch.empty((n, h, w, 2), dtype=torch.float32, device=prev.device)
+        L.check(self._lib.ofb_lk_level_device(self._h, prev.data_ptr(), next.data_ptr(), pitch, pitch * h, w, h, n, win,
+                                              warp_mode, C.c_float(flow_scale),
+                                              cum_in.data_ptr() if cum_in is not None else None, flow_out.data_ptr(),
+                                              cum_out.data_ptr() if cum_out is not None else None, C.c_void_p(stream)))
+        return flow_out
+
+    def lk_level_strip_device(self, prev, next, w: int, y_off: int, h_global: int, out_y0: int, out_y1: int, win: int,
+                              warp_mode: int, flow_scale: float, cum_in, cum_y_off: int, flow_out, cum_out=None,
+                              overflow_flag=None, stream: int = 0):
+        """Row-strip variant: prev/next are (h_local, pitch) uint8 holding global rows [y_off, y_off+h_local)."""
+        h_local, pitch = prev.shape
+        cum_h_local = cum_in.shape[0] if cum_in is not None else 0
+        L.check(self._lib.ofb_lk_level_strip_device(
+            self._h, prev.data_ptr(), next.data_ptr(), pitch, w, h_local, y_off, h_global, out_y0, out_y1, win, warp_mode,
+            C.c_float(flow_scale), cum_in.data_ptr() if cum_in is not None else None, cum_y_off, cum_h_local,
+            flow_out.data_ptr(), cum_out.data_ptr() if cum_out is not None else None,
+            overflow_flag.data_ptr() if overflow_flag is not None else None, C.c_void_p(stream)))
+        return flow_out
+
+
+def planar_to_device(imgs: np.ndarray, device="cuda:0"):
+    """(n, h, w) uint8 numpy -> torch (n, h, pitch) with pitch = align_up(w, 64); padding is zero."""
+    import torch
+
+    n, h, w = imgs.shape
+    pitch = align_up(w, 64)
+    t = torch.zeros((n, h, pitch), dtype=torch.uint8, device=device)
+    t[:, :, :w] = torch.from_numpy(np.ascontiguousarray(imgs)).to(device)
+    return t

@@ -1,0 +1,732 @@
+// ofb_api.cu -- context object and the extern "C" surface declared in include/ofb200.h.
+#include "ofb_common.cuh"
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+namespace ofb {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+} // namespace ofb
+
+// One growable device workspace per context; carved by offset for each call.  Growing it frees the
+// old block (cudaFree synchronises the device), so steady-state calls allocate nothing -- unlike
+// the reference, which does 30 cudaMalloc/cudaFree pairs per level (OptFlowGpu.cu:1105-1124 etc.).
+struct ofb_ctx {
+    int device = 0;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr; // used by the synchronous host-pointer entry points
+    uint8_t *ws = nullptr;
+    size_t ws_bytes = 0;
+    unsigned long long launches = 0;
+};
+
+namespace ofb {
+
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = false;
+    explicit DeviceGuard(int dev)
+    {
+        if (cudaGetDevice(&prev) != cudaSuccess) {
+            prev = -1;
+            set_error("no usable CUDA device: %s", cudaGetErrorString(cudaGetLastError()));
+            return;
+        }
+        if (prev != dev && cudaSetDevice(dev) != cudaSuccess) {
+            set_error("cudaSetDevice(%d) failed: %s", dev, cudaGetErrorString(cudaGetLastError()));
+            return;
+        }
+        ok = true;
+    }
+    ~DeviceGuard()
+    {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+static int ws_reserve(ofb_ctx *c, size_t bytes)
+{
+    if (bytes <= c->ws_bytes) return OFB_OK;
+    if (c->ws) {
+        OFB_CUDA_TRY(cudaDeviceSynchronize());
+        OFB_CUDA_TRY(cudaFree(c->ws));
+        c->ws = nullptr;
+        c->ws_bytes = 0;
+    }
+    const size_t want = align_up(bytes + bytes / 8, 1 << 20);
+    cudaError_t e = cudaMalloc(reinterpret_cast<void **>(&c->ws), want);
+    if (e != cudaSuccess) {
+        set_error("workspace cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e));
+        cudaGetLastError();
+        return OFB_ERR_NOMEM;
+    }
+    c->ws_bytes = want;
+    return OFB_OK;
+}
+
+struct Carver {
+    size_t off = 0;
+    size_t take(size_t bytes)
+    {
+        const size_t o = off;
+        off = align_up(off + bytes, 256);
+        return o;
+    }
+};
+
+static int check_params(const ofb_params *p)
+{
+    if (!p) {
+        set_error("params is NULL");
+        return OFB_ERR_INVALID;
+    }
+    if (p->levels < 1 || p->levels > OFB_MAX_LEVELS) {
+        set_error("levels %d outside 1..%d", p->levels, OFB_MAX_LEVELS);
+        return OFB_ERR_INVALID;
+    }
+    if (p->w < 1 || p->h < 1 || (p->w >> (p->levels - 1)) < 2 || (p->h >> (p->levels - 1)) < 2) {
+        set_error("frame %dx%d too small for %d levels (coarsest level must be at least 2x2)", p->w, p->h, p->levels);
+        return OFB_ERR_INVALID;
+    }
+    if (p->win < 3 || p->win > OFB_MAX_WINDOW || !(p->win & 1)) {
+        set_error("window %d not supported (odd 3..%d)", p->win, OFB_MAX_WINDOW);
+        return OFB_ERR_UNSUPPORTED;
+    }
+    if (p->warp_mode < OFB_WARP_AS_WRITTEN || p->warp_mode > OFB_WARP_BILINEAR) {
+        set_error("unknown warp mode %d", p->warp_mode);
+        return OFB_ERR_INVALID;
+    }
+    if (p->n_pairs < 1) {
+        set_error("n_pairs %d < 1", p->n_pairs);
+        return OFB_ERR_INVALID;
+    }
+    return OFB_OK;
+}
+
+// Pyramids of both frames + coarse-to-fine LK, everything device resident.  `base` is the
+// context workspace region reserved for this call.
+struct PairPlan {
+    int L = 0;
+    int w[OFB_MAX_LEVELS], h[OFB_MAX_LEVELS];
+    size_t pitch[OFB_MAX_LEVELS], istride[OFB_MAX_LEVELS];
+    size_t off_prev[OFB_MAX_LEVELS], off_next[OFB_MAX_LEVELS], off_cum[OFB_MAX_LEVELS];
+    size_t bytes = 0;
+};
+
+static void plan_pairs(const ofb_params *p, PairPlan *pl, Carver *cv)
+{
+    pl->L = p->levels;
+    for (int k = 0; k < p->levels; k++) {
+        pl->w[k] = p->w >> k;
+        pl->h[k] = p->h >> k;
+        pl->pitch[k] = align_up((size_t)pl->w[k], 64);
+        pl->istride[k] = pl->pitch[k] * (size_t)pl->h[k];
+        pl->off_prev[k] = pl->off_next[k] = pl->off_cum[k] = (size_t)-1;
+        if (k >= 1) {
+            pl->off_prev[k] = cv->take(pl->istride[k] * p->n_pairs);
+            pl->off_next[k] = cv->take(pl->istride[k] * p->n_pairs);
+        }
+        if (k >= 1 && k <= p->levels - 2) pl->off_cum[k] = cv->take((size_t)pl->w[k] * pl->h[k] * 8 * p->n_pairs);
+    }
+    pl->bytes = cv->off;
+}
+
+static int run_pairs_device(ofb_ctx *c, const ofb_params *p, const PairPlan &pl, uint8_t *base, const uint8_t *prev0,
+                            const uint8_t *next0, size_t pitch0, size_t istride0, float *const *flow_levels,
+                            float *total_flow, cudaStream_t st)
+{
+    const int L = p->levels, n = p->n_pairs;
+    const uint8_t *pp[OFB_MAX_LEVELS], *pn[OFB_MAX_LEVELS];
+    size_t pitch[OFB_MAX_LEVELS], istr[OFB_MAX_LEVELS];
+    pp[0] = prev0;
+    pn[0] = next0;
+    pitch[0] = pitch0;
+    istr[0] = istride0;
+    for (int k = 1; k < L; k++) {
+        pp[k] = base + pl.off_prev[k];
+        pn[k] = base + pl.off_next[k];
+        pitch[k] = pl.pitch[k];
+        istr[k] = pl.istride[k];
+        int rc = launch_pyr_down(pp[k - 1], pitch[k - 1], istr[k - 1], pl.w[k - 1], pl.h[k - 1],
+                                 const_cast<uint8_t *>(pp[k]), pitch[k], istr[k], n, 1, st, &c->launches);
+        if (rc) return rc;
+        rc = launch_pyr_down(pn[k - 1], pitch[k - 1], istr[k - 1], pl.w[k - 1], pl.h[k - 1], const_cast<uint8_t *>(pn[k]),
+                             pitch[k], istr[k], n, 1, st, &c->launches);
+        if (rc) return rc;
+    }
+    for (int k = L - 1; k >= 0; k--) {
+        LkLevelArgs a{};
+        a.prev = pp[k];
+        a.next = pn[k];
+        a.pitch = pitch[k];
+        a.image_stride = istr[k];
+        a.w = pl.w[k];
+        a.h_local = pl.h[k];
+        a.y_off = 0;
+        a.h_global = pl.h[k];
+        a.out_y0 = 0;
+        a.out_y1 = pl.h[k];
+        a.n_pairs = n;
+        a.win = p->win;
+        a.warp_mode = p->warp_mode;
+        a.flow_scale = p->flow_scale;
+        a.flow_out = flow_levels[k];
+        a.flow_pair_stride = (size_t)pl.w[k] * pl.h[k];
+        a.sm_count = c->sm_count;
+        if (k < L - 1) {
+            // cum_{k+1}: the coarsest level's cumulative flow is its residual flow
+            a.cum_in = (k + 1 == L - 1) ? flow_levels[k + 1] : reinterpret_cast<const float *>(base + pl.off_cum[k + 1]);
+            a.cum_w = pl.w[k + 1];
+            a.cum_h_global = pl.h[k + 1];
+            a.cum_y_off = 0;
+            a.cum_h_local = pl.h[k + 1];
+            a.cum_pair_stride = (size_t)pl.w[k + 1] * pl.h[k + 1];
+        }
+        if (k == 0) a.cum_out = total_flow;
+        else if (k <= L - 2) a.cum_out = reinterpret_cast<float *>(base + pl.off_cum[k]);
+        int rc = launch_lk_level(a, st, &c->launches);
+        if (rc) return rc;
+    }
+    return OFB_OK;
+}
+
+} // namespace ofb
+
+using namespace ofb;
+
+#define OFB_CHECK_CTX(c)                     \
+    do {                                     \
+        if (!(c)) {                          \
+            set_error("context is NULL");    \
+            return OFB_ERR_INVALID;          \
+        }                                    \
+    } while (0)
+#define OFB_GUARD(c)            \
+    DeviceGuard _guard((c)->device); \
+    if (!_guard.ok) return OFB_ERR_CUDA
+
+extern "C" {
+
+const char *ofb_last_error(void) { return g_err; }
+int ofb_version(void) { return 100; }
+
+int ofb_ctx_create(int device, ofb_ctx **out)
+{
+    if (!out) {
+        set_error("out is NULL");
+        return OFB_ERR_INVALID;
+    }
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev < 1) {
+        set_error("no CUDA device available (%s); this library has no CPU fallback",
+                  e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+        cudaGetLastError();
+        return OFB_ERR_CUDA;
+    }
+    if (device < 0 || device >= ndev) {
+        set_error("device %d outside 0..%d", device, ndev - 1);
+        return OFB_ERR_INVALID;
+    }
+    DeviceGuard g(device);
+    if (!g.ok) return OFB_ERR_CUDA;
+    cudaDeviceProp prop;
+    OFB_CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) {
+        set_error("device %d is sm_%d%d; this library is built for sm_100a (B200) only", device, prop.major, prop.minor);
+        return OFB_ERR_UNSUPPORTED;
+    }
+    ofb_ctx *c = new (std::nothrow) ofb_ctx();
+    if (!c) {
+        set_error("out of host memory");
+        return OFB_ERR_NOMEM;
+    }
+    c->device = device;
+    c->sm_count = prop.multiProcessorCount;
+    e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) {
+        set_error("cudaStreamCreate failed: %s", cudaGetErrorString(e));
+        delete c;
+        return OFB_ERR_CUDA;
+    }
+    *out = c;
+    return OFB_OK;
+}
+
+int ofb_ctx_destroy(ofb_ctx *c)
+{
+    OFB_CHECK_CTX(c);
+    {
+        DeviceGuard g(c->device);
+        if (g.ok) {
+            cudaDeviceSynchronize();
+            if (c->ws) cudaFree(c->ws);
+            if (c->stream) cudaStreamDestroy(c->stream);
+        }
+    }
+    delete c;
+    return OFB_OK;
+}
+
+int ofb_ctx_device(const ofb_ctx *c, int *device)
+{
+    OFB_CHECK_CTX(c);
+    if (device) *device = c->device;
+    return OFB_OK;
+}
+
+int ofb_ctx_sm_count(const ofb_ctx *c, int *sm_count)
+{
+    OFB_CHECK_CTX(c);
+    if (sm_count) *sm_count = c->sm_count;
+    return OFB_OK;
+}
+
+int ofb_ctx_launch_count(const ofb_ctx *c, unsigned long long *count)
+{
+    OFB_CHECK_CTX(c);
+    if (count) *count = c->launches;
+    return OFB_OK;
+}
+
+int ofb_host_alloc(void **ptr, size_t bytes)
+{
+    if (!ptr) {
+        set_error("ptr is NULL");
+        return OFB_ERR_INVALID;
+    }
+    cudaError_t e = cudaHostAlloc(ptr, bytes, cudaHostAllocDefault);
+    if (e != cudaSuccess) {
+        set_error("cudaHostAlloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
+        cudaGetLastError();
+        return OFB_ERR_NOMEM;
+    }
+    return OFB_OK;
+}
+
+int ofb_host_free(void *ptr)
+{
+    if (ptr) OFB_CUDA_TRY(cudaFreeHost(ptr));
+    return OFB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// device-resident hot path
+// ---------------------------------------------------------------------------------------------
+int ofb_flow_pairs_device(ofb_ctx *c, const ofb_params *p, const uint8_t *prev_d, const uint8_t *next_d,
+                          size_t pitch_bytes, size_t image_stride_bytes, float *const *flow_levels_d, float *total_flow_d,
+                          void *stream)
+{
+    OFB_CHECK_CTX(c);
+    int rc = check_params(p);
+    if (rc) return rc;
+    if (!prev_d || !next_d || !flow_levels_d) {
+        set_error("NULL frame or flow pointer");
+        return OFB_ERR_INVALID;
+    }
+    for (int k = 0; k < p->levels; k++)
+        if (!flow_levels_d[k]) {
+            set_error("flow_levels_d[%d] is NULL", k);
+            return OFB_ERR_INVALID;
+        }
+    if (pitch_bytes < (size_t)p->w || (p->n_pairs > 1 && image_stride_bytes < pitch_bytes * (size_t)p->h)) {
+        set_error("pitch %zu / image stride %zu too small for %dx%d", pitch_bytes, image_stride_bytes, p->w, p->h);
+        return OFB_ERR_INVALID;
+    }
+    OFB_GUARD(c);
+    Carver cv;
+    PairPlan pl;
+    plan_pairs(p, &pl, &cv);
+    rc = ws_reserve(c, pl.bytes);
+    if (rc) return rc;
+    return run_pairs_device(c, p, pl, c->ws, prev_d, next_d, pitch_bytes, image_stride_bytes, flow_levels_d, total_flow_d,
+                            static_cast<cudaStream_t>(stream));
+}
+
+int ofb_pyr_down_device(ofb_ctx *c, const uint8_t *src_d, size_t src_pitch, size_t src_image_stride, int sw, int sh,
+                        uint8_t *dst_d, size_t dst_pitch, size_t dst_image_stride, int n_images, void *stream)
+{
+    OFB_CHECK_CTX(c);
+    if (!src_d || !dst_d) {
+        set_error("NULL image pointer");
+        return OFB_ERR_INVALID;
+    }
+    OFB_GUARD(c);
+    return launch_pyr_down(src_d, src_pitch, src_image_stride, sw, sh, dst_d, dst_pitch, dst_image_stride, n_images, 1,
+                           static_cast<cudaStream_t>(stream), &c->launches);
+}
+
+int ofb_lk_level_device(ofb_ctx *c, const uint8_t *prev_d, const uint8_t *next_d, size_t pitch_bytes,
+                        size_t image_stride_bytes, int w, int h, int n_pairs, int win, int warp_mode, float flow_scale,
+                        const float *cum_in_d, float *flow_out_d, float *cum_out_d, void *stream)
+{
+    OFB_CHECK_CTX(c);
+    if (!prev_d || !next_d || !flow_out_d) {
+        set_error("NULL image or flow pointer");
+        return OFB_ERR_INVALID;
+    }
+    OFB_GUARD(c);
+    LkLevelArgs a{};
+    a.prev = prev_d;
+    a.next = next_d;
+    a.pitch = pitch_bytes;
+    a.image_stride = image_stride_bytes;
+    a.w = w;
+    a.h_local = h;
+    a.y_off = 0;
+    a.h_global = h;
+    a.out_y0 = 0;
+    a.out_y1 = h;
+    a.n_pairs = n_pairs;
+    a.win = win;
+    a.warp_mode = warp_mode;
+    a.flow_scale = flow_scale;
+    a.cum_in = cum_in_d;
+    a.cum_w = w >> 1;
+    a.cum_h_global = h >> 1;
+    a.cum_y_off = 0;
+    a.cum_h_local = h >> 1;
+    a.cum_pair_stride = (size_t)(w >> 1) * (h >> 1);
+    a.flow_out = flow_out_d;
+    a.cum_out = cum_out_d;
+    a.flow_pair_stride = (size_t)w * h;
+    a.sm_count = c->sm_count;
+    if (cum_in_d && ((w >> 1) < 1 || (h >> 1) < 1)) {
+        set_error("level %dx%d has no coarser level", w, h);
+        return OFB_ERR_INVALID;
+    }
+    return launch_lk_level(a, static_cast<cudaStream_t>(stream), &c->launches);
+}
+
+int ofb_lk_level_strip_device(ofb_ctx *c, const uint8_t *prev_d, const uint8_t *next_d, size_t pitch_bytes, int w,
+                              int h_local, int y_off, int h_global, int out_y0, int out_y1, int win, int warp_mode,
+                              float flow_scale, const float *cum_in_d, int cum_y_off, int cum_h_local, float *flow_out_d,
+                              float *cum_out_d, int *reach_overflow_d, void *stream)
+{
+    OFB_CHECK_CTX(c);
+    if (!prev_d || !next_d || !flow_out_d) {
+        set_error("NULL image or flow pointer");
+        return OFB_ERR_INVALID;
+    }
+    if (cum_in_d && warp_mode == OFB_WARP_AS_WRITTEN) {
+        set_error("OFB_WARP_AS_WRITTEN needs pixel (0,0) of every coarser level and is not available on row strips");
+        return OFB_ERR_UNSUPPORTED;
+    }
+    if (y_off < 0 || y_off + h_local > h_global) {
+        set_error("strip rows [%d,%d) outside the level height %d", y_off, y_off + h_local, h_global);
+        return OFB_ERR_INVALID;
+    }
+    OFB_GUARD(c);
+    LkLevelArgs a{};
+    a.prev = prev_d;
+    a.next = next_d;
+    a.pitch = pitch_bytes;
+    a.image_stride = pitch_bytes * (size_t)h_local;
+    a.w = w;
+    a.h_local = h_local;
+    a.y_off = y_off;
+    a.h_global = h_global;
+    a.out_y0 = out_y0;
+    a.out_y1 = out_y1;
+    a.n_pairs = 1;
+    a.win = win;
+    a.warp_mode = warp_mode;
+    a.flow_scale = flow_scale;
+    a.cum_in = cum_in_d;
+    a.cum_w = w >> 1;
+    a.cum_h_global = h_global >> 1;
+    a.cum_y_off = cum_y_off;
+    a.cum_h_local = cum_h_local;
+    a.cum_pair_stride = 0;
+    a.flow_out = flow_out_d;
+    a.cum_out = cum_out_d;
+    a.flow_pair_stride = 0;
+    a.reach_overflow = reach_overflow_d;
+    a.sm_count = c->sm_count;
+    return launch_lk_level(a, static_cast<cudaStream_t>(stream), &c->launches);
+}
+
+int ofb_c3_to_planar_device(ofb_ctx *c, const uint8_t *src_c3_d, int w, int h, int n_images, uint8_t *dst_d,
+                            size_t dst_pitch, size_t dst_image_stride, void *stream)
+{
+    OFB_CHECK_CTX(c);
+    if (!src_c3_d || !dst_d) {
+        set_error("NULL image pointer");
+        return OFB_ERR_INVALID;
+    }
+    OFB_GUARD(c);
+    return launch_c3_to_planar(src_c3_d, w, h, n_images, dst_d, dst_pitch, dst_image_stride,
+                               static_cast<cudaStream_t>(stream), &c->launches);
+}
+
+// ---------------------------------------------------------------------------------------------
+// host-pointer entry points (synchronous)
+// ---------------------------------------------------------------------------------------------
+int ofb_gauss_pyramid_host_u8c3(ofb_ctx *c, unsigned char **pyramid, int w, int h, int levels)
+{
+    OFB_CHECK_CTX(c);
+    if (!pyramid || levels < 1 || levels > OFB_MAX_LEVELS || w < 1 || h < 1 || (w >> (levels - 1)) < 1 ||
+        (h >> (levels - 1)) < 1) {
+        set_error("gauss_pyramid: bad arguments (w %d h %d levels %d)", w, h, levels);
+        return OFB_ERR_INVALID;
+    }
+    for (int k = 0; k < levels; k++)
+        if (!pyramid[k]) {
+            set_error("gauss_pyramid: pyramid[%d] is NULL", k);
+            return OFB_ERR_INVALID;
+        }
+    if (levels == 1) return OFB_OK;
+    OFB_GUARD(c);
+    Carver cv;
+    size_t off[OFB_MAX_LEVELS];
+    for (int k = 0; k < levels; k++) off[k] = cv.take((size_t)(w >> k) * (h >> k) * 3);
+    int rc = ws_reserve(c, cv.off);
+    if (rc) return rc;
+    cudaStream_t st = c->stream;
+    OFB_CUDA_TRY(cudaMemcpyAsync(c->ws + off[0], pyramid[0], (size_t)w * h * 3, cudaMemcpyHostToDevice, st));
+    for (int k = 1; k < levels; k++) {
+        const int sw = w >> (k - 1), sh = h >> (k - 1), dw = w >> k, dh = h >> k;
+        rc = launch_pyr_down(c->ws + off[k - 1], (size_t)sw * 3, 0, sw, sh, c->ws + off[k], (size_t)dw * 3, 0, 1, 3, st,
+                             &c->launches);
+        if (rc) return rc;
+        OFB_CUDA_TRY(cudaMemcpyAsync(pyramid[k], c->ws + off[k], (size_t)dw * dh * 3, cudaMemcpyDeviceToHost, st));
+    }
+    OFB_CUDA_TRY(cudaStreamSynchronize(st));
+    return OFB_OK;
+}
+
+int ofb_calc_opt_flow_host_u8c3(ofb_ctx *c, const unsigned char *prev, const unsigned char *next, int w, int h,
+                                float **optFlowPyramid, int level, int maxLevel, int win, int warp_mode, float flow_scale)
+{
+    OFB_CHECK_CTX(c);
+    if (!prev || !next || !optFlowPyramid || w < 1 || h < 1 || level < 0 || level >= maxLevel ||
+        maxLevel > OFB_MAX_LEVELS) {
+        set_error("calc_opt_flow: bad arguments (w %d h %d level %d maxLevel %d)", w, h, level, maxLevel);
+        return OFB_ERR_INVALID;
+    }
+    for (int k = level; k < maxLevel; k++) {
+        if (!optFlowPyramid[k]) {
+            set_error("calc_opt_flow: optFlowPyramid[%d] is NULL", k);
+            return OFB_ERR_INVALID;
+        }
+        if ((w >> (k - level)) < 1 || (h >> (k - level)) < 1) {
+            set_error("calc_opt_flow: level %d of a %dx%d level-%d image is empty", k, w, h, level);
+            return OFB_ERR_INVALID;
+        }
+    }
+    OFB_GUARD(c);
+    const size_t pitch = align_up((size_t)w, 64);
+    Carver cv;
+    const size_t off_c3 = cv.take((size_t)w * h * 3 * 2);
+    const size_t off_p = cv.take(pitch * h), off_n = cv.take(pitch * h);
+    const size_t off_flow = cv.take((size_t)w * h * 8);
+    size_t off_res[OFB_MAX_LEVELS], off_cum[OFB_MAX_LEVELS];
+    for (int k = level + 1; k < maxLevel; k++) {
+        const size_t n = (size_t)(w >> (k - level)) * (h >> (k - level));
+        off_res[k] = cv.take(n * 8);
+        off_cum[k] = cv.take(n * 8);
+    }
+    int rc = ws_reserve(c, cv.off);
+    if (rc) return rc;
+    cudaStream_t st = c->stream;
+    uint8_t *B = c->ws;
+    const size_t c3 = (size_t)w * h * 3;
+    OFB_CUDA_TRY(cudaMemcpyAsync(B + off_c3, prev, c3, cudaMemcpyHostToDevice, st));
+    OFB_CUDA_TRY(cudaMemcpyAsync(B + off_c3 + c3, next, c3, cudaMemcpyHostToDevice, st));
+    rc = launch_c3_to_planar(B + off_c3, w, h, 1, B + off_p, pitch, pitch * h, st, &c->launches);
+    if (rc) return rc;
+    rc = launch_c3_to_planar(B + off_c3 + c3, w, h, 1, B + off_n, pitch, pitch * h, st, &c->launches);
+    if (rc) return rc;
+    // cumulative flow of level+1 from the residual flows the caller holds (main.cu:136-147)
+    const float *cum_in = nullptr;
+    for (int k = maxLevel - 1; k > level; k--) {
+        const int wk = w >> (k - level), hk = h >> (k - level);
+        OFB_CUDA_TRY(cudaMemcpyAsync(B + off_res[k], optFlowPyramid[k], (size_t)wk * hk * 8, cudaMemcpyHostToDevice, st));
+        if (k == maxLevel - 1) {
+            cum_in = reinterpret_cast<const float *>(B + off_res[k]);
+        } else {
+            rc = launch_compose_cum(reinterpret_cast<const float *>(B + off_res[k]), cum_in, wk, hk, 1,
+                                    reinterpret_cast<float *>(B + off_cum[k]), st, &c->launches);
+            if (rc) return rc;
+            cum_in = reinterpret_cast<const float *>(B + off_cum[k]);
+        }
+    }
+    LkLevelArgs a{};
+    a.prev = B + off_p;
+    a.next = B + off_n;
+    a.pitch = pitch;
+    a.image_stride = pitch * h;
+    a.w = w;
+    a.h_local = h;
+    a.h_global = h;
+    a.out_y1 = h;
+    a.n_pairs = 1;
+    a.win = win;
+    a.warp_mode = warp_mode;
+    a.flow_scale = flow_scale;
+    a.cum_in = cum_in;
+    a.cum_w = w >> 1;
+    a.cum_h_global = h >> 1;
+    a.cum_h_local = h >> 1;
+    a.flow_out = reinterpret_cast<float *>(B + off_flow);
+    a.sm_count = c->sm_count;
+    rc = launch_lk_level(a, st, &c->launches);
+    if (rc) return rc;
+    OFB_CUDA_TRY(cudaMemcpyAsync(optFlowPyramid[level], B + off_flow, (size_t)w * h * 8, cudaMemcpyDeviceToHost, st));
+    OFB_CUDA_TRY(cudaStreamSynchronize(st));
+    return OFB_OK;
+}
+
+int ofb_conv_3ch_1ch_u8_f32_host(ofb_ctx *c, const unsigned char *src_h, int w, int h, float *dest_h, const float *mask,
+                                 int mw, int mh)
+{
+    OFB_CHECK_CTX(c);
+    if (!src_h || !dest_h || !mask || w < 1 || h < 1) {
+        set_error("conv: bad arguments");
+        return OFB_ERR_INVALID;
+    }
+    OFB_GUARD(c);
+    Carver cv;
+    const size_t off_s = cv.take((size_t)w * h * 3), off_d = cv.take((size_t)w * h * 4);
+    int rc = ws_reserve(c, cv.off);
+    if (rc) return rc;
+    cudaStream_t st = c->stream;
+    OFB_CUDA_TRY(cudaMemcpyAsync(c->ws + off_s, src_h, (size_t)w * h * 3, cudaMemcpyHostToDevice, st));
+    rc = launch_conv_c3_f32(c->ws + off_s, w, h, reinterpret_cast<float *>(c->ws + off_d), mask, mw, mh, st, &c->launches);
+    if (rc) return rc;
+    OFB_CUDA_TRY(cudaMemcpyAsync(dest_h, c->ws + off_d, (size_t)w * h * 4, cudaMemcpyDeviceToHost, st));
+    OFB_CUDA_TRY(cudaStreamSynchronize(st));
+    return OFB_OK;
+}
+
+int ofb_srm_1ch_f32_host(ofb_ctx *c, const float *arr1_h, const float *arr2_h, int w, int h, int ww, int wh,
+                         float *dest_h)
+{
+    OFB_CHECK_CTX(c);
+    if (!arr1_h || !arr2_h || !dest_h || w < 1 || h < 1) {
+        set_error("srm: bad arguments");
+        return OFB_ERR_INVALID;
+    }
+    OFB_GUARD(c);
+    const size_t n = (size_t)w * h * 4;
+    Carver cv;
+    const size_t oa = cv.take(n), ob = cv.take(n), od = cv.take(n);
+    int rc = ws_reserve(c, cv.off);
+    if (rc) return rc;
+    cudaStream_t st = c->stream;
+    OFB_CUDA_TRY(cudaMemcpyAsync(c->ws + oa, arr1_h, n, cudaMemcpyHostToDevice, st));
+    const float *bdev = reinterpret_cast<const float *>(c->ws + oa);
+    if (arr2_h != arr1_h) {
+        OFB_CUDA_TRY(cudaMemcpyAsync(c->ws + ob, arr2_h, n, cudaMemcpyHostToDevice, st));
+        bdev = reinterpret_cast<const float *>(c->ws + ob);
+    }
+    rc = launch_srm_f32(reinterpret_cast<const float *>(c->ws + oa), bdev, w, h, ww, wh,
+                        reinterpret_cast<float *>(c->ws + od), st, &c->launches);
+    if (rc) return rc;
+    OFB_CUDA_TRY(cudaMemcpyAsync(dest_h, c->ws + od, n, cudaMemcpyDeviceToHost, st));
+    OFB_CUDA_TRY(cudaStreamSynchronize(st));
+    return OFB_OK;
+}
+
+int ofb_inverse_matrix_f32_host(ofb_ctx *c, const float *sumIx2, const float *sumIy2, const float *sumIxIy,
+                                const float *sumIxIt, const float *sumIyIt, float **optFlowPyramid, int level, int w, int h)
+{
+    OFB_CHECK_CTX(c);
+    if (!sumIx2 || !sumIy2 || !sumIxIy || !sumIxIt || !sumIyIt || !optFlowPyramid || level < 0 || !optFlowPyramid[level] ||
+        w < 1 || h < 1) {
+        set_error("inverse_matrix: bad arguments");
+        return OFB_ERR_INVALID;
+    }
+    OFB_GUARD(c);
+    const size_t n = (size_t)w * h * 4;
+    Carver cv;
+    size_t o[5];
+    for (int k = 0; k < 5; k++) o[k] = cv.take(n);
+    const size_t of = cv.take(2 * n);
+    int rc = ws_reserve(c, cv.off);
+    if (rc) return rc;
+    cudaStream_t st = c->stream;
+    const float *src[5] = {sumIx2, sumIy2, sumIxIy, sumIxIt, sumIyIt};
+    for (int k = 0; k < 5; k++) OFB_CUDA_TRY(cudaMemcpyAsync(c->ws + o[k], src[k], n, cudaMemcpyHostToDevice, st));
+    rc = launch_inverse_f32(reinterpret_cast<const float *>(c->ws + o[0]), reinterpret_cast<const float *>(c->ws + o[1]),
+                            reinterpret_cast<const float *>(c->ws + o[2]), reinterpret_cast<const float *>(c->ws + o[3]),
+                            reinterpret_cast<const float *>(c->ws + o[4]), reinterpret_cast<float *>(c->ws + of), w * h,
+                            st, &c->launches);
+    if (rc) return rc;
+    OFB_CUDA_TRY(cudaMemcpyAsync(optFlowPyramid[level], c->ws + of, 2 * n, cudaMemcpyDeviceToHost, st));
+    OFB_CUDA_TRY(cudaStreamSynchronize(st));
+    return OFB_OK;
+}
+
+int ofb_flow_pairs_host(ofb_ctx *c, const ofb_params *p, const unsigned char *prev_h, const unsigned char *next_h,
+                        int channels, float *const *flow_levels_h)
+{
+    OFB_CHECK_CTX(c);
+    int rc = check_params(p);
+    if (rc) return rc;
+    if (!prev_h || !next_h || !flow_levels_h || (channels != 1 && channels != 3)) {
+        set_error("flow_pairs_host: bad arguments (channels %d)", channels);
+        return OFB_ERR_INVALID;
+    }
+    for (int k = 0; k < p->levels; k++)
+        if (!flow_levels_h[k]) {
+            set_error("flow_levels_h[%d] is NULL", k);
+            return OFB_ERR_INVALID;
+        }
+    OFB_GUARD(c);
+    const int n = p->n_pairs;
+    const size_t pitch0 = align_up((size_t)p->w, 64), istride0 = pitch0 * (size_t)p->h;
+    Carver cv;
+    const size_t off_p0 = cv.take(istride0 * n), off_n0 = cv.take(istride0 * n);
+    const size_t c3 = (size_t)p->w * p->h * 3;
+    const size_t off_c3 = (channels == 3) ? cv.take(c3 * n * 2) : 0;
+    size_t off_flow[OFB_MAX_LEVELS];
+    for (int k = 0; k < p->levels; k++) off_flow[k] = cv.take((size_t)(p->w >> k) * (p->h >> k) * 8 * n);
+    PairPlan pl;
+    const size_t plan_base = cv.off;
+    Carver cv2;
+    plan_pairs(p, &pl, &cv2);
+    rc = ws_reserve(c, plan_base + pl.bytes);
+    if (rc) return rc;
+    cudaStream_t st = c->stream;
+    uint8_t *B = c->ws;
+    if (channels == 1) {
+        OFB_CUDA_TRY(cudaMemcpy2DAsync(B + off_p0, pitch0, prev_h, (size_t)p->w, (size_t)p->w, (size_t)p->h * n,
+                                       cudaMemcpyHostToDevice, st));
+        OFB_CUDA_TRY(cudaMemcpy2DAsync(B + off_n0, pitch0, next_h, (size_t)p->w, (size_t)p->w, (size_t)p->h * n,
+                                       cudaMemcpyHostToDevice, st));
+    } else {
+        OFB_CUDA_TRY(cudaMemcpyAsync(B + off_c3, prev_h, c3 * n, cudaMemcpyHostToDevice, st));
+        OFB_CUDA_TRY(cudaMemcpyAsync(B + off_c3 + c3 * n, next_h, c3 * n, cudaMemcpyHostToDevice, st));
+        rc = launch_c3_to_planar(B + off_c3, p->w, p->h, n, B + off_p0, pitch0, istride0, st, &c->launches);
+        if (rc) return rc;
+        rc = launch_c3_to_planar(B + off_c3 + c3 * n, p->w, p->h, n, B + off_n0, pitch0, istride0, st, &c->launches);
+        if (rc) return rc;
+    }
+    float *flow_d[OFB_MAX_LEVELS];
+    for (int k = 0; k < p->levels; k++) flow_d[k] = reinterpret_cast<float *>(B + off_flow[k]);
+    rc = run_pairs_device(c, p, pl, B + plan_base, B + off_p0, B + off_n0, pitch0, istride0, flow_d, nullptr, st);
+    if (rc) return rc;
+    for (int k = p->levels - 1; k >= 0; k--)
+        OFB_CUDA_TRY(cudaMemcpyAsync(flow_levels_h[k], flow_d[k], (size_t)(p->w >> k) * (p->h >> k) * 8 * n,
+                                     cudaMemcpyDeviceToHost, st));
+    OFB_CUDA_TRY(cudaStreamSynchronize(st));
+    return OFB_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,74 @@
+// ofb_common.cuh -- shared declarations of the sm_100a kernels and their launchers.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/ofb200.h"
+
+namespace ofb {
+
+// ---- error plumbing (ofb_api.cu) -----------------------------------------------------------
+void set_error(const char *fmt, ...);
+#define OFB_CUDA_TRY(expr)                                                                              \
+    do {                                                                                                \
+        cudaError_t _e = (expr);                                                                        \
+        if (_e != cudaSuccess) {                                                                        \
+            ofb::set_error("%s:%d: %s failed: %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+            return OFB_ERR_CUDA;                                                                        \
+        }                                                                                               \
+    } while (0)
+
+// ---- fused LK level (lk_level.cu) ----------------------------------------------------------
+struct LkLevelArgs {
+    const uint8_t *prev;   // planar u8, local rows [0, h_local)
+    const uint8_t *next;
+    size_t pitch;          // bytes, multiple of 16
+    size_t image_stride;   // bytes between pairs, multiple of 16
+    int w;                 // width
+    int h_local;           // rows held by the buffers
+    int y_off;             // global row of local row 0
+    int h_global;          // height of the whole level
+    int out_y0, out_y1;    // local rows to produce
+    int n_pairs;
+    int win;               // odd 3..19
+    int warp_mode;         // OFB_WARP_*
+    float flow_scale;
+    const float *cum_in;   // coarser cumulative flow (float2), NULL => coarsest level, no warp
+    int cum_w;             // coarser level width
+    int cum_h_global;      // coarser level height (whole level)
+    int cum_y_off;         // global coarse row of cum_in's row 0
+    int cum_h_local;       // rows held by cum_in
+    size_t cum_pair_stride;   // float2 elements between pairs
+    float *flow_out;       // float2, local rows (same origin as prev/next)
+    float *cum_out;        // optional
+    size_t flow_pair_stride;  // float2 elements between pairs (flow_out and cum_out)
+    int *reach_overflow;   // optional device flag: a warp sample fell outside the local rows
+    int sm_count;
+};
+int launch_lk_level(const LkLevelArgs &a, cudaStream_t stream, unsigned long long *launches);
+
+// ---- pyramid (pyramid.cu) ------------------------------------------------------------------
+int launch_pyr_down(const uint8_t *src, size_t src_pitch, size_t src_stride, int sw, int sh, uint8_t *dst,
+                    size_t dst_pitch, size_t dst_stride, int n_images, int channels, cudaStream_t stream,
+                    unsigned long long *launches);
+
+// ---- stage kernels + layout helpers (stages.cu) --------------------------------------------
+int launch_c3_to_planar(const uint8_t *src_c3, int w, int h, int n_images, uint8_t *dst, size_t dst_pitch,
+                        size_t dst_stride, cudaStream_t stream, unsigned long long *launches);
+int launch_conv_c3_f32(const uint8_t *src_c3, int w, int h, float *dst, const float *mask_host, int mw, int mh,
+                       cudaStream_t stream, unsigned long long *launches);
+int launch_srm_f32(const float *a, const float *b, int w, int h, int ww, int wh, float *dst, cudaStream_t stream,
+                   unsigned long long *launches);
+int launch_inverse_f32(const float *sxx, const float *syy, const float *sxy, const float *sxt, const float *syt,
+                       float *flow, int n, cudaStream_t stream, unsigned long long *launches);
+int launch_compose_cum(const float *flow_k, const float *cum_coarser, int w, int h, int n_pairs, float *cum_out,
+                       cudaStream_t stream, unsigned long long *launches);
+
+// cuTensorMapEncodeTiled resolved through the runtime (no link-time libcuda dependency).
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                    const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+PFN_encodeTiled get_encode_tiled();
+
+} // namespace ofb

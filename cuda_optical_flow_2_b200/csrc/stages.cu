@@ -1,0 +1,193 @@
+// stages.cu -- the reference's stand-alone stage functions and layout helpers.
+// These back the host-pointer drop-in wrappers (gpu::conv_3ch_1ch_tiled_uchar_float,
+// gpu::srm_1ch_float, gpu::inverse_matrix_float); the hot path uses the fused kernel instead.
+// Each keeps the reference's floating-point operation order, so results are bit-identical to the
+// reference kernels for any float input, not only for integer-valued derivatives.
+#include "ofb_common.cuh"
+
+namespace ofb {
+
+struct Mask25 {
+    float m[25];
+};
+
+// g_conv_3ch_1ch_constant_uchar_float, OptFlowGpu.cu:1040-1090: correlation of channel 0 with an
+// mw x mh mask, out-of-image taps and zero mask entries skipped, fp32 fma in row-major tap order.
+// The mask travels as a kernel argument (the reference's shared __constant__ mask makes its API
+// non re-entrant, OptFlowGpu.cu:190,1109).
+__global__ void __launch_bounds__(256)
+conv_c3_f32_kernel(const uint8_t *__restrict__ src, int w, int h, float *__restrict__ dst, Mask25 mk, int mw, int mh)
+{
+    const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
+    if (x >= w || y >= h) return;
+    const int hmw = mw >> 1, hmh = mh >> 1;
+    float tmp = 0.0f;
+    for (int i = 0; i < mh; i++) {
+        const int ty = y - hmh + i;
+        if (ty < 0 || ty >= h) continue;
+        for (int j = 0; j < mw; j++) {
+            const int tx = x - hmw + j;
+            if (tx < 0 || tx >= w) continue;
+            const float m = mk.m[i * mw + j];
+            if (m == 0) continue;
+            tmp = __fmaf_rn((float)__ldg(src + ((size_t)ty * w + tx) * 3), m, tmp);
+        }
+    }
+    dst[(size_t)y * w + x] = tmp;
+}
+
+int launch_conv_c3_f32(const uint8_t *src_c3, int w, int h, float *dst, const float *mask_host, int mw, int mh,
+                       cudaStream_t stream, unsigned long long *launches)
+{
+    if (w < 1 || h < 1 || mw < 1 || mh < 1 || mw * mh > 25) {
+        set_error("conv: bad geometry (w %d h %d mask %dx%d, at most 25 taps)", w, h, mw, mh);
+        return OFB_ERR_INVALID;
+    }
+    Mask25 mk;
+    for (int i = 0; i < 25; i++) mk.m[i] = (i < mw * mh) ? mask_host[i] : 0.0f;
+    dim3 block(32, 8), grid((unsigned)((w + 31) / 32), (unsigned)((h + 7) / 8));
+    conv_c3_f32_kernel<<<grid, block, 0, stream>>>(src_c3, w, h, dst, mk, mw, mh);
+    OFB_CUDA_TRY(cudaGetLastError());
+    if (launches) ++*launches;
+    return OFB_OK;
+}
+
+// g_srm_1ch_float, OptFlowGpu.cu:1549-1588: windowed sum of a*b, out-of-image taps skipped,
+// `tmp += a*b` (one fma per tap) in row-major tap order.  A 32x8 output tile stages its
+// (32+ww-1) x (8+wh-1) footprint of both inputs in shared memory; out-of-image positions are
+// flagged so that the tap order and skipping match the reference exactly.
+constexpr int SRM_BX = 32, SRM_BY = 8, SRM_MAXW = 32; // window up to 32x32
+__global__ void __launch_bounds__(SRM_BX *SRM_BY)
+srm_f32_kernel(const float *__restrict__ a, const float *__restrict__ b, int w, int h, int ww, int wh,
+               float *__restrict__ dst)
+{
+    extern __shared__ float sm[];
+    const int tw = SRM_BX + ww - 1, th = SRM_BY + wh - 1;
+    float *sa = sm, *sb = sm + tw * th;
+    const int hww = ww >> 1, hwh = wh >> 1;
+    const int bx0 = blockIdx.x * SRM_BX - hww, by0 = blockIdx.y * SRM_BY - hwh;
+    const int tid = threadIdx.y * SRM_BX + threadIdx.x;
+    for (int t = tid; t < tw * th; t += SRM_BX * SRM_BY) {
+        const int ty = t / tw, tx = t - ty * tw;
+        const int gx = bx0 + tx, gy = by0 + ty;
+        const bool in = gx >= 0 && gx < w && gy >= 0 && gy < h;
+        sa[t] = in ? __ldg(a + (size_t)gy * w + gx) : 0.0f;
+        sb[t] = in ? __ldg(b + (size_t)gy * w + gx) : 0.0f;
+    }
+    __syncthreads();
+    const int x = blockIdx.x * SRM_BX + threadIdx.x, y = blockIdx.y * SRM_BY + threadIdx.y;
+    if (x >= w || y >= h) return;
+    float tmp = 0.0f;
+    for (int p = 0; p < wh; p++) {
+        const int gy = y - hwh + p;
+        if (gy < 0 || gy >= h) continue;
+        const float *ra = sa + (threadIdx.y + p) * tw + threadIdx.x, *rb = sb + (threadIdx.y + p) * tw + threadIdx.x;
+        for (int q = 0; q < ww; q++) {
+            const int gx = x - hww + q;
+            if (gx < 0 || gx >= w) continue;
+            tmp = __fmaf_rn(ra[q], rb[q], tmp);
+        }
+    }
+    dst[(size_t)y * w + x] = tmp;
+}
+
+int launch_srm_f32(const float *a, const float *b, int w, int h, int ww, int wh, float *dst, cudaStream_t stream,
+                   unsigned long long *launches)
+{
+    if (w < 1 || h < 1 || ww < 1 || wh < 1 || ww > SRM_MAXW || wh > SRM_MAXW) {
+        set_error("srm: bad geometry (w %d h %d window %dx%d, at most %dx%d)", w, h, ww, wh, SRM_MAXW, SRM_MAXW);
+        return OFB_ERR_INVALID;
+    }
+    const size_t smem = (size_t)(SRM_BX + ww - 1) * (SRM_BY + wh - 1) * 2 * sizeof(float);
+    dim3 block(SRM_BX, SRM_BY), grid((unsigned)((w + SRM_BX - 1) / SRM_BX), (unsigned)((h + SRM_BY - 1) / SRM_BY));
+    srm_f32_kernel<<<grid, block, smem, stream>>>(a, b, w, h, ww, wh, dst);
+    OFB_CUDA_TRY(cudaGetLastError());
+    if (launches) ++*launches;
+    return OFB_OK;
+}
+
+// g_inv_matrix_float, OptFlowGpu.cu:1819-1846, same double-precision operation order (lk_solve
+// takes exact integers; this variant takes the reference's float sums).
+__global__ void __launch_bounds__(256)
+inverse_f32_kernel(const float *__restrict__ sxx, const float *__restrict__ syy, const float *__restrict__ sxy,
+                   const float *__restrict__ sxt, const float *__restrict__ syt, float2 *__restrict__ flow, int n)
+{
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= n) return;
+    const double a = (double)sxx[i], b = (double)sxy[i], d = (double)syy[i], tx = (double)sxt[i], ty = (double)syt[i];
+    const double det = __fma_rn(a, d, -__dmul_rn(b, b));
+    const double prefix = 1.0 / det;
+    const double ap = __dmul_rn(a, prefix), bp = __dmul_rn(b, prefix), dp = __dmul_rn(d, prefix);
+    flow[i] = make_float2((float)__fma_rn(bp, ty, -__dmul_rn(dp, tx)), (float)__fma_rn(bp, tx, -__dmul_rn(ap, ty)));
+}
+
+int launch_inverse_f32(const float *sxx, const float *syy, const float *sxy, const float *sxt, const float *syt,
+                       float *flow, int n, cudaStream_t stream, unsigned long long *launches)
+{
+    if (n < 1) {
+        set_error("inverse: empty input");
+        return OFB_ERR_INVALID;
+    }
+    inverse_f32_kernel<<<(n + 255) / 256, 256, 0, stream>>>(sxx, syy, sxy, sxt, syt, reinterpret_cast<float2 *>(flow), n);
+    OFB_CUDA_TRY(cudaGetLastError());
+    if (launches) ++*launches;
+    return OFB_OK;
+}
+
+// Channel 0 of 3-channel interleaved u8 -> planar pitched u8.
+__global__ void __launch_bounds__(256)
+c3_to_planar_kernel(const uint8_t *__restrict__ src, int w, int h, uint8_t *__restrict__ dst, size_t dst_pitch,
+                    size_t dst_stride)
+{
+    const int x = blockIdx.x * 256 + threadIdx.x, y = blockIdx.y;
+    if (x >= w) return;
+    const size_t img = blockIdx.z;
+    dst[img * dst_stride + (size_t)y * dst_pitch + x] = __ldg(src + (img * (size_t)w * h + (size_t)y * w + x) * 3);
+}
+
+int launch_c3_to_planar(const uint8_t *src_c3, int w, int h, int n_images, uint8_t *dst, size_t dst_pitch,
+                        size_t dst_stride, cudaStream_t stream, unsigned long long *launches)
+{
+    if (w < 1 || h < 1 || h > 65535 || n_images < 1 || n_images > 65535) {
+        set_error("c3_to_planar: bad geometry (w %d h %d images %d)", w, h, n_images);
+        return OFB_ERR_INVALID;
+    }
+    dim3 grid((unsigned)((w + 255) / 256), (unsigned)h, (unsigned)n_images);
+    c3_to_planar_kernel<<<grid, 256, 0, stream>>>(src_c3, w, h, dst, dst_pitch, dst_stride);
+    OFB_CUDA_TRY(cudaGetLastError());
+    if (launches) ++*launches;
+    return OFB_OK;
+}
+
+// cum_k = 2*cum_{k+1}[i>>1, j>>1] + flow_k : the composition rule of main.cu:136-147 applied
+// coarse to fine (power-of-two scaling is exact, so this equals the reference's running sum).
+__global__ void __launch_bounds__(256)
+compose_cum_kernel(const float2 *__restrict__ flow, const float2 *__restrict__ coarser, int w, int h, int cw, int ch,
+                   float2 *__restrict__ out)
+{
+    const int x = blockIdx.x * 256 + threadIdx.x, y = blockIdx.y;
+    if (x >= w) return;
+    const size_t pair = blockIdx.z;
+    const float2 f = flow[pair * (size_t)w * h + (size_t)y * w + x];
+    float2 c = make_float2(0.0f, 0.0f);
+    if (coarser) c = __ldg(coarser + pair * (size_t)cw * ch + (size_t)min(y >> 1, ch - 1) * cw + min(x >> 1, cw - 1));
+    out[pair * (size_t)w * h + (size_t)y * w + x] = make_float2(2.0f * c.x + f.x, 2.0f * c.y + f.y);
+}
+
+int launch_compose_cum(const float *flow_k, const float *cum_coarser, int w, int h, int n_pairs, float *cum_out,
+                       cudaStream_t stream, unsigned long long *launches)
+{
+    if (w < 1 || h < 1 || h > 65535 || n_pairs < 1 || n_pairs > 65535) {
+        set_error("compose_cum: bad geometry (w %d h %d pairs %d)", w, h, n_pairs);
+        return OFB_ERR_INVALID;
+    }
+    dim3 grid((unsigned)((w + 255) / 256), (unsigned)h, (unsigned)n_pairs);
+    compose_cum_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const float2 *>(flow_k),
+                                                 reinterpret_cast<const float2 *>(cum_coarser), w, h, w >> 1, h >> 1,
+                                                 reinterpret_cast<float2 *>(cum_out));
+    OFB_CUDA_TRY(cudaGetLastError());
+    if (launches) ++*launches;
+    return OFB_OK;
+}
+
+} // namespace ofb

@@ -1,0 +1,167 @@
+/*
+ * ofb200.h -- C ABI of the B200-native dense pyramidal Lucas-Kanade path.
+ *
+ * Drop-in boundary for ONE path of Kr-Stam/CUDA_Optical_Flow_2: Gaussian pyramid -> Ix/Iy/It ->
+ * windowed structure-tensor sums -> per-pixel 2x2 solve -> coarse-to-fine flow upsample + warp.
+ * Every entry point names the reference interface it replaces (file:line into the reference tree).
+ * Plain pointers and sizes only; no C++ or torch types.  All functions return OFB_OK (0) or an
+ * OFB_ERR_* code; ofb_last_error() gives the message of the calling thread's last failure.
+ * There is no CPU fallback: without a CUDA device every compute entry point fails with OFB_ERR_CUDA.
+ *
+ * Layouts
+ *   host images (reference layout): u8, 3 interleaved channels, tightly packed, channels equal
+ *       (OptFlowGpu.cu:58-59); the LK stages read channel 0 only (OptFlowGpu.cu:1081).
+ *   device images (hot path):       u8, planar, row pitch a multiple of 16 bytes, base 16-byte
+ *       aligned; image i of a batch starts at base + i*image_stride_bytes (multiple of 16).
+ *   flow: float (u,v) interleaved per pixel, tightly packed rows (OptFlowGpu.cu:1844-1845);
+ *       level k of a pyramid is (w>>k) x (h>>k) pixels (main.cu:95-104).
+ */
+#ifndef OFB200_H
+#define OFB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OFB_OK 0
+#define OFB_ERR_INVALID 1     /* bad argument */
+#define OFB_ERR_CUDA 2        /* CUDA runtime / driver failure (including "no device") */
+#define OFB_ERR_UNSUPPORTED 3 /* valid request outside the built configuration set */
+#define OFB_ERR_NOMEM 4
+
+/* How next_k is shifted back by the coarser flow before a level is solved
+ * (cpu::shift_back_pyramid, OptFlowCPU.cpp:241-282, called at OptFlowGpu.cu:1918-1922). */
+#define OFB_WARP_AS_WRITTEN 0 /* bug-compatible: the flow of pixel (0,0) of every coarser level, nearest */
+#define OFB_WARP_NEAREST 1    /* per-pixel coarser flow (index i>>off as main.cu:141-143), nearest sample */
+#define OFB_WARP_BILINEAR 2   /* per-pixel coarser flow, 8.8 fixed-point bilinear sample (north_star) */
+
+#define OFB_MAX_LEVELS 8
+#define OFB_MAX_WINDOW 19 /* odd windows 3..19; 19 is what OptFlowGpu.cu:1944-1945 hard-codes */
+
+typedef struct ofb_ctx ofb_ctx; /* owns device workspace, streams and TMA descriptors for one GPU */
+
+/* Parameters of one pyramidal solve (the hard-coded values of main.cu:192 and OptFlowGpu.cu:1944). */
+typedef struct ofb_params {
+    int w, h;         /* level-0 width / height in pixels */
+    int levels;       /* pyramid levels, 1..OFB_MAX_LEVELS (main.cu:192 uses 4) */
+    int win;          /* LK window, odd, 3..OFB_MAX_WINDOW */
+    int warp_mode;    /* OFB_WARP_* */
+    float flow_scale; /* multiplies the coarser flow before the warp; 1.0f = the reference (Q5) */
+    int n_pairs;      /* frame pairs in the batch (>= 1) */
+} ofb_params;
+
+const char *ofb_last_error(void);
+int ofb_version(void);
+
+/* One context per GPU (and per host thread that drives it).  Replaces the reference's implicit
+ * device 0 + per-call cudaMalloc/cudaFree (OptFlowGpu.cu:1105-1106, 1123-1124). */
+int ofb_ctx_create(int device, ofb_ctx **out);
+int ofb_ctx_destroy(ofb_ctx *ctx);
+int ofb_ctx_device(const ofb_ctx *ctx, int *device);
+int ofb_ctx_sm_count(const ofb_ctx *ctx, int *sm_count);
+
+/* ------------------------------------------------------------------------------------------
+ * Device-resident hot path (what the metric is quoted on).  Asynchronous on `stream`
+ * (a cudaStream_t passed as void*; NULL = the legacy default stream).
+ * ---------------------------------------------------------------------------------------- */
+
+/* Whole path for a batch of pairs: pyramids of both frames (gpu::gauss_pyramid,
+ * OptFlowGpu.cu:1262-1271) then the coarse-to-fine loop of main.cu:256-262 calling the fused
+ * per-level kernel (gpu::calc_opt_flow, OptFlowGpu.cu:1909-1979).
+ *   prev_d / next_d : level-0 planar u8 frames, n_pairs images each.
+ *   flow_levels_d[k]: out, RESIDUAL flow of level k (what the reference leaves in
+ *                     optFlowPyramid[k]); n_pairs * (h>>k) * (w>>k) * 2 floats.
+ *   total_flow_d    : optional out (may be NULL), the composition rule of main.cu:136-147 at
+ *                     level 0: sum_k 2^k * flow_k[i>>k, j>>k]; n_pairs * h * w * 2 floats. */
+int ofb_flow_pairs_device(ofb_ctx *ctx, const ofb_params *p, const uint8_t *prev_d, const uint8_t *next_d,
+                          size_t pitch_bytes, size_t image_stride_bytes, float *const *flow_levels_d,
+                          float *total_flow_d, void *stream);
+
+/* One pyramid step for n_images planar images: dst = (sw>>1) x (sh>>1).
+ * Replaces gpu::gauss_pyramid_level / g_gauss_pyramid (OptFlowGpu.cu:1235-1259, 1198-1232). */
+int ofb_pyr_down_device(ofb_ctx *ctx, const uint8_t *src_d, size_t src_pitch, size_t src_image_stride, int sw, int sh,
+                        uint8_t *dst_d, size_t dst_pitch, size_t dst_image_stride, int n_images, void *stream);
+
+/* One fused LK level on device-resident planar images: warp next by the coarser cumulative flow,
+ * Ix/Iy/It, five window sums, solve.  Replaces the body of gpu::calc_opt_flow for one level
+ * (OptFlowGpu.cu:1909-1979) without its host round trips.
+ *   cum_in_d : cumulative flow of the next-coarser level ((w>>1) x (h>>1) float2 per pair:
+ *              cum_{k+1} = flow_{k+1} + 2*cum_{k+2}[i>>1, j>>1]); NULL for the coarsest level
+ *              (not warped, OptFlowGpu.cu:1918).
+ *   flow_out_d: residual flow of this level.  cum_out_d: optional, 2*cum_in[i>>1,j>>1] + flow. */
+int ofb_lk_level_device(ofb_ctx *ctx, const uint8_t *prev_d, const uint8_t *next_d, size_t pitch_bytes,
+                        size_t image_stride_bytes, int w, int h, int n_pairs, int win, int warp_mode, float flow_scale,
+                        const float *cum_in_d, float *flow_out_d, float *cum_out_d, void *stream);
+
+/* Row-strip variant of ofb_lk_level_device for frames partitioned across GPUs.  The buffers hold
+ * rows [y_off, y_off + h_local) of a (w x h_global) level; flow is produced for local rows
+ * [out_y0, out_y1).  cum_in_d holds coarse rows starting at global coarse row cum_y_off
+ * (cum_h_local rows).  Rows of prev/next needed beyond the local buffer must be halo rows already
+ * exchanged by the caller; only the global image border is zero padded. */
+int ofb_lk_level_strip_device(ofb_ctx *ctx, const uint8_t *prev_d, const uint8_t *next_d, size_t pitch_bytes, int w,
+                              int h_local, int y_off, int h_global, int out_y0, int out_y1, int win, int warp_mode,
+                              float flow_scale, const float *cum_in_d, int cum_y_off, int cum_h_local,
+                              float *flow_out_d, float *cum_out_d, int *reach_overflow_d, void *stream);
+
+/* Layout helpers: channel 0 of 3-channel interleaved u8 -> planar pitched u8 and back
+ * (the reference keeps 3 equal channels; grayscale_avg OptFlowGpu.cu:58-59). */
+int ofb_c3_to_planar_device(ofb_ctx *ctx, const uint8_t *src_c3_d, int w, int h, int n_images, uint8_t *dst_d,
+                            size_t dst_pitch, size_t dst_image_stride, void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Host-pointer entry points with the reference's argument meaning (synchronous, like the
+ * reference's blocking cudaMemcpy).  These are what the C++ `namespace gpu` wrappers in
+ * include/OptFlowGpuB200.hpp forward to.
+ * ---------------------------------------------------------------------------------------- */
+
+/* gpu::gauss_pyramid(unsigned char** pyramid, int w, int h, int levels, mask, mw, mh),
+ * OptFlowGpu.cuh:21 / OptFlowGpu.cu:1262.  3-channel interleaved host levels, pyramid[0] is the
+ * input; the reference ignores its mask arguments (fixed 3x3 binomial), so they are not taken. */
+int ofb_gauss_pyramid_host_u8c3(ofb_ctx *ctx, unsigned char **pyramid, int w, int h, int levels);
+
+/* gpu::calc_opt_flow(prev, next, w, h, optFlowPyramid, level, maxLevel), OptFlowGpu.cuh:33 /
+ * OptFlowGpu.cu:1909, with the window (hard-coded 19 there), warp mode and flow scale exposed.
+ * prev/next are level `level` images (3-ch interleaved host); optFlowPyramid[k > level] are read,
+ * optFlowPyramid[level] is written; w,h are this level's size. */
+int ofb_calc_opt_flow_host_u8c3(ofb_ctx *ctx, const unsigned char *prev, const unsigned char *next, int w, int h,
+                                float **optFlowPyramid, int level, int maxLevel, int win, int warp_mode,
+                                float flow_scale);
+
+/* gpu::conv_3ch_1ch_tiled_uchar_float(src_h, w, h, dest_h, mask_t, mw, mh), OptFlowGpu.cuh:17 /
+ * OptFlowGpu.cu:1100: correlation of channel 0 with an mw x mh (<= 5x5) mask, zero padding. */
+int ofb_conv_3ch_1ch_u8_f32_host(ofb_ctx *ctx, const unsigned char *src_h, int w, int h, float *dest_h,
+                                 const float *mask, int mw, int mh);
+
+/* gpu::srm_1ch_float(arr1_h, arr2_h, w, h, ww, wh, dest_h), OptFlowGpu.cuh:25 / OptFlowGpu.cu:1597:
+ * windowed sum of products, fp32 running sum in the reference's tap order. */
+int ofb_srm_1ch_f32_host(ofb_ctx *ctx, const float *arr1_h, const float *arr2_h, int w, int h, int ww, int wh,
+                         float *dest_h);
+
+/* gpu::inverse_matrix_float(sumIx2, sumIy2, sumIxIy, sumIxIt, sumIyIt, optFlowPyramid, level, w, h),
+ * OptFlowGpu.cuh:31 / OptFlowGpu.cu:1858: per-pixel 2x2 solve in double, writes optFlowPyramid[level]. */
+int ofb_inverse_matrix_f32_host(ofb_ctx *ctx, const float *sumIx2, const float *sumIy2, const float *sumIxIy,
+                                const float *sumIxIt, const float *sumIyIt, float **optFlowPyramid, int level, int w,
+                                int h);
+
+/* The loop of main.cu:246-262 for a batch of pairs with HOST buffers: upload level-0 frames
+ * (channels = 3: reference layout, channel 0 is used; channels = 1: planar gray), build both
+ * pyramids, run all levels, download the residual flow of every level.
+ *   flow_levels_h[k]: n_pairs * (h>>k) * (w>>k) * 2 floats.  Pinned host memory makes the copies
+ * asynchronous; pageable memory works too. */
+int ofb_flow_pairs_host(ofb_ctx *ctx, const ofb_params *p, const unsigned char *prev_h, const unsigned char *next_h,
+                        int channels, float *const *flow_levels_h);
+
+/* Pinned host memory helpers for callers without a CUDA runtime of their own. */
+int ofb_host_alloc(void **ptr, size_t bytes);
+int ofb_host_free(void *ptr);
+
+/* Number of kernels this library has launched on this context since creation (bench bookkeeping). */
+int ofb_ctx_launch_count(const ofb_ctx *ctx, unsigned long long *count);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OFB200_H */

@@ -1,0 +1,221 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on the same inputs.
+
+Bars:
+  * pyramid levels: byte-exact;
+  * flow against the oracle with EXACT window sums: bit-for-bit equal (the kernel does the same
+    integer arithmetic and the same double-precision solve), non-finite pixels in the same places;
+  * flow against the oracle with the reference's fp32-sequential window sums: equal wherever every
+    window sum stays below 2^24 (the fp32 sums are then exact), otherwise max |du|,|dv| <= TOL_ABS
+    + TOL_REL*|ref| on pixels where both are finite.
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+TOL_ABS = 1e-4  # px, stated tolerance on u and v (and so on end-point error up to sqrt(2))
+TOL_REL = 1e-5
+
+
+def _torch():
+    import torch
+
+    return torch
+
+
+def assert_flow_identical(got: np.ndarray, ref: np.ndarray, what: str = ""):
+    assert got.shape == ref.shape, what
+    fg, fr = np.isfinite(got), np.isfinite(ref)
+    assert np.array_equal(fg, fr), f"{what}: finite masks differ at {np.argwhere(fg != fr)[:5]}"
+    assert np.array_equal(np.isnan(got), np.isnan(ref)), f"{what}: NaN masks differ"
+    bad = fg & (got != ref)
+    if bad.any():
+        idx = np.argwhere(bad)[:5]
+        raise AssertionError(f"{what}: {bad.sum()} of {bad.size} values differ, first at {idx.tolist()}: "
+                             f"got {got[tuple(idx[0])]!r} ref {ref[tuple(idx[0])]!r}, max abs diff "
+                             f"{np.abs(got[bad] - ref[bad]).max():.3e}")
+    inf = ~fg & ~np.isnan(got)
+    assert np.array_equal(got[inf], ref[inf]), f"{what}: infinities differ in sign"
+
+
+def assert_flow_close(got: np.ndarray, ref: np.ndarray, what: str = ""):
+    both = np.isfinite(got) & np.isfinite(ref)
+    # where the reference's own fp32 rounding made one side non-finite the other may be huge: require
+    # agreement of the masks except on (near-)singular pixels, which the caller avoids via textured input
+    assert (np.isfinite(got) == np.isfinite(ref)).mean() > 0.9999, what
+    d = np.abs(got[both] - ref[both])
+    lim = TOL_ABS + TOL_REL * np.abs(ref[both])
+    assert (d <= lim).all(), f"{what}: max abs diff {d.max():.3e} exceeds tolerance"
+
+
+def frames(oracle, w, h, dx=1.0, dy=0.5, cell=4, seed=1234):
+    return oracle.make_frame(w, h, 0.0, 0.0, cell, seed), oracle.make_frame(w, h, dx, dy, cell, seed)
+
+
+# ------------------------------------------------------------------------------------ pyramid
+@pytest.mark.parametrize("w,h", [(640, 480), (1920, 1080), (101, 77), (64, 34), (258, 130)])
+def test_pyr_down_device_byte_exact(ctx, oracle, w, h):
+    torch = _torch()
+    from cuda_optical_flow_2_b200 import planar_to_device
+
+    imgs = np.stack([oracle.make_frame(w, h, 0, 0, 4, 100 + i) for i in range(3)])
+    d = ctx.pyr_down_device(planar_to_device(imgs), w)
+    torch.cuda.synchronize()
+    got = d.cpu().numpy()[:, :, : w >> 1]
+    for i in range(3):
+        assert np.array_equal(got[i], oracle.pyr_down(imgs[i])), f"image {i}"
+
+
+# ------------------------------------------------------------------------------------ single level
+@pytest.mark.parametrize("w,h,win", [(640, 480, 5), (640, 480, 9), (320, 240, 19), (203, 117, 15), (64, 64, 3),
+                                     (131, 59, 7), (250, 40, 11), (96, 200, 13), (128, 128, 17), (1920, 1080, 9)])
+def test_lk_level_coarsest_identical_to_exact_oracle(ctx, oracle, w, h, win):
+    torch = _torch()
+    from cuda_optical_flow_2_b200 import planar_to_device
+
+    prev, nxt = frames(oracle, w, h)
+    flow = ctx.lk_level_device(planar_to_device(prev[None]), planar_to_device(nxt[None]), w, win, cum_in=None)
+    torch.cuda.synchronize()
+    got = flow.cpu().numpy()[0]
+    ref = oracle.lk_level(prev, nxt, win, oracle.SUMS_EXACT)
+    assert_flow_identical(got, ref, f"{w}x{h} win {win}")
+
+
+@pytest.mark.parametrize("w,h,win,cell", [(640, 480, 5, 8), (640, 480, 9, 8), (640, 480, 19, 2), (320, 240, 15, 4)])
+def test_lk_level_vs_reference_fp32_sums(ctx, oracle, w, h, win, cell):
+    """Against the reference's own rounding (fp32 sequential window sums)."""
+    torch = _torch()
+    from cuda_optical_flow_2_b200 import planar_to_device
+
+    prev, nxt = frames(oracle, w, h, cell=cell)
+    flow = ctx.lk_level_device(planar_to_device(prev[None]), planar_to_device(nxt[None]), w, win, cum_in=None)
+    torch.cuda.synchronize()
+    got = flow.cpu().numpy()[0]
+    ref = oracle.lk_level(prev, nxt, win, oracle.SUMS_F32_SEQUENTIAL)
+    sums = oracle.lk_level_sums(prev, nxt, win)
+    if max(np.abs(s).max() for s in sums) < 2 ** 24:
+        assert_flow_identical(got, ref, "sums < 2^24: fp32 sums are exact")
+    else:
+        assert_flow_close(got, ref, "sums >= 2^24")
+
+
+def test_flat_image_nonfinite_mask(ctx, oracle):
+    """det == 0 windows: the reference writes inf/NaN (no threshold, OptFlowGpu.cu:1835); so do we."""
+    torch = _torch()
+    from cuda_optical_flow_2_b200 import planar_to_device
+
+    w, h = 160, 96
+    prev, nxt = frames(oracle, w, h)
+    prev[20:70, 30:120] = 77
+    nxt[20:70, 30:120] = 77
+    flow = ctx.lk_level_device(planar_to_device(prev[None]), planar_to_device(nxt[None]), w, 9)
+    torch.cuda.synchronize()
+    got = flow.cpu().numpy()[0]
+    ref = oracle.lk_level(prev, nxt, 9, oracle.SUMS_EXACT)
+    assert (~np.isfinite(ref)).sum() > 100
+    assert_flow_identical(got, ref)
+
+
+# ------------------------------------------------------------------------------------ multi level
+@pytest.mark.parametrize("mode", [0, 1, 2])
+@pytest.mark.parametrize("w,h,levels,win", [(640, 480, 4, 9), (322, 246, 3, 5), (1920, 1080, 3, 9)])
+def test_flow_pairs_device_identical_to_oracle(ctx, oracle, mode, w, h, levels, win):
+    torch = _torch()
+    from cuda_optical_flow_2_b200 import planar_to_device
+
+    n = 2
+    prevs = np.stack([oracle.make_frame(w, h, 0, 0, 8, 500 + i) for i in range(n)])
+    nexts = np.stack([oracle.make_frame(w, h, 2.5 + i, -1.25, 8, 500 + i) for i in range(n)])
+    total = torch.empty((n, h, w, 2), dtype=torch.float32, device="cuda")
+    flows = ctx.flow_pairs_device(planar_to_device(prevs), planar_to_device(nexts), w, levels, win, warp_mode=mode,
+                                  total_flow=total)
+    torch.cuda.synchronize()
+    for i in range(n):
+        ref, cums = oracle.flow_pair(prevs[i], nexts[i], levels, win, mode, oracle.SUMS_EXACT, 1.0, want_cum=True)
+        for k in range(levels - 1, -1, -1):
+            assert_flow_identical(flows[k][i].cpu().numpy(), ref[k], f"pair {i} level {k} mode {mode}")
+        assert_flow_identical(total[i].cpu().numpy(), cums[0], f"pair {i} total flow")
+
+
+def test_flow_scale(ctx, oracle):
+    torch = _torch()
+    from cuda_optical_flow_2_b200 import planar_to_device
+
+    w, h, levels, win = 320, 240, 3, 9
+    prev, nxt = frames(oracle, w, h, 3.0, 1.0, 8)
+    flows = ctx.flow_pairs_device(planar_to_device(prev[None]), planar_to_device(nxt[None]), w, levels, win, warp_mode=2,
+                                  flow_scale=8.0 / 15.0)
+    torch.cuda.synchronize()
+    ref = oracle.flow_pair(prev, nxt, levels, win, 2, oracle.SUMS_EXACT, np.float32(8.0 / 15.0))
+    for k in range(levels):
+        assert_flow_identical(flows[k][0].cpu().numpy(), ref[k], f"level {k}")
+
+
+# ------------------------------------------------------------------------------------ host wrappers
+def test_gauss_pyramid_host_c3(ctx, oracle):
+    w, h, levels = 640, 480, 4
+    rng = np.random.default_rng(5)
+    img = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)  # channels differ: each is processed independently
+    pyr = [img.copy()] + [np.zeros((h >> k, w >> k, 3), np.uint8) for k in range(1, levels)]
+    ctx.gauss_pyramid(pyr, w, h, levels)
+    for c in range(3):
+        ref = oracle.gauss_pyramid(np.ascontiguousarray(img[:, :, c]), levels)
+        for k in range(levels):
+            assert np.array_equal(pyr[k][:, :, c], ref[k]), f"channel {c} level {k}"
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2])
+def test_calc_opt_flow_host_loop(ctx, oracle, mode):
+    """The main.cu:256-262 loop through the drop-in per-level entry point."""
+    w, h, levels, win = 320, 240, 3, 9
+    prev, nxt = frames(oracle, w, h, 2.0, 1.0, 8)
+    pp = oracle.gauss_pyramid(prev, levels)
+    pn = oracle.gauss_pyramid(nxt, levels)
+    flows = [np.zeros((h >> k, w >> k, 2), np.float32) for k in range(levels)]
+    for k in range(levels - 1, -1, -1):
+        ctx.calc_opt_flow(oracle.to_c3(pp[k]), oracle.to_c3(pn[k]), w >> k, h >> k, flows, k, levels, win=win,
+                          warp_mode=mode)
+    ref = oracle.flow_pair(prev, nxt, levels, win, mode, oracle.SUMS_EXACT)
+    for k in range(levels):
+        assert_flow_identical(flows[k], ref[k], f"level {k} mode {mode}")
+
+
+def test_stage_functions_host(ctx, oracle):
+    w, h, win = 200, 120, 7
+    prev, nxt = frames(oracle, w, h)
+    c3 = oracle.to_c3(prev)
+    ix = ctx.conv_3ch_1ch_tiled_uchar_float(c3, w, h, oracle.DX, 3, 3)
+    iy = ctx.conv_3ch_1ch_tiled_uchar_float(c3, w, h, oracle.DY, 3, 3)
+    it1 = ctx.conv_3ch_1ch_tiled_uchar_float(c3, w, h, oracle.DT, 3, 3)
+    it2 = ctx.conv_3ch_1ch_tiled_uchar_float(oracle.to_c3(nxt), w, h, oracle.DT, 3, 3)
+    assert np.array_equal(ix, oracle.conv(prev, oracle.DX))
+    assert np.array_equal(iy, oracle.conv(prev, oracle.DY))
+    assert np.array_equal(it1, oracle.conv(prev, oracle.DT))
+    it = it2 - it1
+    rng = np.random.default_rng(1)
+    fa = (rng.standard_normal((h, w)) * 1000).astype(np.float32)  # non-integer floats: fp32 order must match too
+    fb = (rng.standard_normal((h, w)) * 1000).astype(np.float32)
+    assert np.array_equal(ctx.srm_1ch_float(fa, fb, w, h, win, win), oracle.srm_f32(fa, fb, win, win))
+    sums = [ctx.srm_1ch_float(a, b, w, h, win, win) for a, b in ((ix, ix), (iy, iy), (ix, iy), (ix, it), (iy, it))]
+    for s, (a, b) in zip(sums, ((ix, ix), (iy, iy), (ix, iy), (ix, it), (iy, it))):
+        assert np.array_equal(s, oracle.srm_f32(a, b, win, win))
+    flows = [np.zeros((h, w, 2), np.float32)]
+    ctx.inverse_matrix_float(*sums, flows, 0, w, h)
+    assert_flow_identical(flows[0], oracle.solve_f32(*sums))
+    # 5x5 mask with zeros, through the generic path
+    m5 = np.arange(25, dtype=np.float32).reshape(5, 5) - 12
+    assert np.array_equal(ctx.conv_3ch_1ch_tiled_uchar_float(c3, w, h, m5, 5, 5), oracle.conv(prev, m5))
+
+
+def test_flow_pairs_host(ctx, oracle):
+    w, h, levels, win = 256, 192, 3, 9
+    prevs = np.stack([oracle.make_frame(w, h, 0, 0, 8, 900 + i) for i in range(3)])
+    nexts = np.stack([oracle.make_frame(w, h, 1.5, 2.0 - i, 8, 900 + i) for i in range(3)])
+    got1 = ctx.flow_pairs_host(prevs, nexts, levels, win)
+    got3 = ctx.flow_pairs_host(np.stack([oracle.to_c3(p) for p in prevs]), np.stack([oracle.to_c3(p) for p in nexts]),
+                               levels, win)
+    for i in range(3):
+        ref = oracle.flow_pair(prevs[i], nexts[i], levels, win, 2, oracle.SUMS_EXACT)
+        for k in range(levels):
+            assert_flow_identical(got1[k][i], ref[k], f"planar pair {i} level {k}")
+            assert_flow_identical(got3[k][i], ref[k], f"c3 pair {i} level {k}")
