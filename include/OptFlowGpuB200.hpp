@@ -1,0 +1,115 @@
+// OptFlowGpuB200.hpp -- C++ drop-in for the pyramidal-LK subset of the reference's OptFlowGpu.cuh.
+//
+// Same namespace, names and signatures as the reference declarations, so main.cu-style callers
+// compile unchanged against this header + libofb200.so:
+//   gpu::gauss_pyramid                    OptFlowGpu.cuh:21   (callers main.cu:209, 250)
+//   gpu::calc_opt_flow                    OptFlowGpu.cuh:33   (caller  main.cu:260)
+//   gpu::conv_3ch_1ch_tiled_uchar_float   OptFlowGpu.cuh:17
+//   gpu::srm_1ch_float                    OptFlowGpu.cuh:25
+//   gpu::inverse_matrix_float             OptFlowGpu.cuh:31
+// Differences, all deliberate (SURVEY.md Q-list):
+//   * the functions stay `void` for source compatibility, but a failure is no longer silent: it is
+//     printed to stderr and kept in gpu::last_status() / ofb_last_error() (the reference checks no
+//     CUDA error at all);
+//   * the LK window (hard-coded 19 at OptFlowGpu.cu:1944-1945), the warp mode and the flow scale are
+//     process-wide options set with gpu::set_lk_options(); the defaults reproduce the reference
+//     (19, warp as written, scale 1);
+//   * no per-call cudaMalloc/cudaFree: one lazily created context per process owns the workspace.
+#pragma once
+#include <cstdio>
+
+#include "ofb200.h"
+
+namespace gpu {
+
+struct LkOptions {
+    int win = 19;
+    int warp_mode = OFB_WARP_AS_WRITTEN;
+    float flow_scale = 1.0f;
+    int device = 0;
+};
+
+inline LkOptions &lk_options()
+{
+    static LkOptions o;
+    return o;
+}
+inline void set_lk_options(int win, int warp_mode, float flow_scale = 1.0f)
+{
+    lk_options().win = win;
+    lk_options().warp_mode = warp_mode;
+    lk_options().flow_scale = flow_scale;
+}
+inline int &last_status()
+{
+    static int s = OFB_OK;
+    return s;
+}
+inline ofb_ctx *default_context()
+{
+    static ofb_ctx *ctx = nullptr;
+    if (!ctx) {
+        int rc = ofb_ctx_create(lk_options().device, &ctx);
+        if (rc != OFB_OK) {
+            last_status() = rc;
+            std::fprintf(stderr, "[ofb200] cannot create context: %s\n", ofb_last_error());
+            ctx = nullptr;
+        }
+    }
+    return ctx;
+}
+inline void report(const char *what, int rc)
+{
+    last_status() = rc;
+    if (rc != OFB_OK) std::fprintf(stderr, "[ofb200] %s failed (%d): %s\n", what, rc, ofb_last_error());
+}
+
+// OptFlowGpu.cuh:21.  mask/mw/mh are accepted and ignored exactly like the reference ignores them
+// (its kernel uses the fixed __constant__ binomial, OptFlowGpu.cu:1193-1196).
+inline void gauss_pyramid(unsigned char **pyramid, int w, int h, int levels, const float * /*mask*/, int /*mw*/,
+                          int /*mh*/)
+{
+    ofb_ctx *c = default_context();
+    if (!c) return;
+    report("gauss_pyramid", ofb_gauss_pyramid_host_u8c3(c, pyramid, w, h, levels));
+}
+
+// OptFlowGpu.cuh:33.
+inline void calc_opt_flow(const unsigned char *prev, unsigned char *next, int w, int h, float **optFlowPyramid,
+                          int level, int maxLevel)
+{
+    ofb_ctx *c = default_context();
+    if (!c) return;
+    const LkOptions &o = lk_options();
+    report("calc_opt_flow", ofb_calc_opt_flow_host_u8c3(c, prev, next, w, h, optFlowPyramid, level, maxLevel, o.win,
+                                                       o.warp_mode, o.flow_scale));
+}
+
+// OptFlowGpu.cuh:17.
+inline void conv_3ch_1ch_tiled_uchar_float(const unsigned char *src_h, int w, int h, float *dest_h,
+                                           const float *mask_t, int mw, int mh)
+{
+    ofb_ctx *c = default_context();
+    if (!c) return;
+    report("conv_3ch_1ch_tiled_uchar_float", ofb_conv_3ch_1ch_u8_f32_host(c, src_h, w, h, dest_h, mask_t, mw, mh));
+}
+
+// OptFlowGpu.cuh:25.
+inline void srm_1ch_float(const float *arr1_h, const float *arr2_h, int w, int h, int ww, int wh, float *dest_h)
+{
+    ofb_ctx *c = default_context();
+    if (!c) return;
+    report("srm_1ch_float", ofb_srm_1ch_f32_host(c, arr1_h, arr2_h, w, h, ww, wh, dest_h));
+}
+
+// OptFlowGpu.cuh:31.
+inline void inverse_matrix_float(float *sumIx2, float *sumIy2, float *sumIxIy, float *sumIxIt, float *sumIyIt,
+                                 float **optFlowPyramid, int level, int w, int h)
+{
+    ofb_ctx *c = default_context();
+    if (!c) return;
+    report("inverse_matrix_float",
+           ofb_inverse_matrix_f32_host(c, sumIx2, sumIy2, sumIxIy, sumIxIt, sumIyIt, optFlowPyramid, level, w, h));
+}
+
+} // namespace gpu
