@@ -11,11 +11,13 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libofb200.so")
+# OFB200_LIB lets a developer point at an experimental build of the same library
+LIB_PATH = os.environ.get("OFB200_LIB") or os.path.join(_HERE, "libofb200.so")
 
 OFB_OK, OFB_ERR_INVALID, OFB_ERR_CUDA, OFB_ERR_UNSUPPORTED, OFB_ERR_NOMEM = 0, 1, 2, 3, 4
 WARP_AS_WRITTEN, WARP_NEAREST, WARP_BILINEAR = 0, 1, 2
 MAX_LEVELS, MAX_WINDOW = 8, 19
+PROFILE_PYRAMID = 100
 
 u8p = C.POINTER(C.c_uint8)
 f32p = C.POINTER(C.c_float)
@@ -44,6 +46,8 @@ SIGNATURES = {
     "ofb_ctx_device": (C.c_int, [_vp, i32p]),
     "ofb_ctx_sm_count": (C.c_int, [_vp, i32p]),
     "ofb_ctx_launch_count": (C.c_int, [_vp, C.POINTER(C.c_ulonglong)]),
+    "ofb_ctx_profile_enable": (C.c_int, [_vp, C.c_int]),
+    "ofb_ctx_profile_read": (C.c_int, [_vp, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_ulonglong)]),
     "ofb_flow_pairs_device": (C.c_int, [_vp, C.POINTER(OfbParams), _vp, _vp, _sz, _sz, C.POINTER(_vp), _vp, _vp]),
     "ofb_pyr_down_device": (C.c_int, [_vp, _vp, _sz, _sz, C.c_int, C.c_int, _vp, _sz, _sz, C.c_int, _vp]),
     "ofb_lk_level_device": (C.c_int, [_vp, _vp, _vp, _sz, _sz, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float,

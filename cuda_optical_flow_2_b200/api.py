@@ -81,6 +81,16 @@ class Context:
         L.check(self._lib.ofb_ctx_launch_count(self._h, C.byref(v)))
         return v.value
 
+    def profile_enable(self, on: bool = True) -> None:
+        """CUDA-event timing around each fused-LK launch (tag = level) and the pyramid build."""
+        L.check(self._lib.ofb_ctx_profile_enable(self._h, 1 if on else 0))
+
+    def profile_read(self, tag: int) -> tuple[float, int]:
+        """(summed milliseconds, number of records) for a tag: a pyramid level or PROFILE_PYRAMID."""
+        ms, n = C.c_double(), C.c_ulonglong()
+        L.check(self._lib.ofb_ctx_profile_read(self._h, int(tag), C.byref(ms), C.byref(n)))
+        return ms.value, n.value
+
     # ---------------------------------------------------------------- reference-named host API
     def gauss_pyramid(self, pyramid: Sequence[np.ndarray], w: int, h: int, levels: int) -> None:
         """gpu::gauss_pyramid (OptFlowGpu.cu:1262): fills pyramid[1..levels-1] from pyramid[0] in place.

@@ -81,7 +81,7 @@ static int launch_one(const LkLevelArgs &a, cudaStream_t stream, unsigned long l
 
     LkKernelParams p;
     p.next = a.next;
-    p.pitch = a.pitch;
+    p.pitch = (int)a.pitch;
     p.image_stride = a.image_stride;
     p.w = a.w;
     p.h_local = a.h_local;
@@ -91,7 +91,8 @@ static int launch_one(const LkLevelArgs &a, cudaStream_t stream, unsigned long l
     p.out_y1 = a.out_y1;
     p.rows_per_block = rows_per_block;
     p.as_written = (a.warp_mode == OFB_WARP_AS_WRITTEN) ? 1 : 0;
-    p.flow_scale = a.flow_scale;
+    p.scale2 = 2.0f * a.flow_scale;
+    p.scale512 = 512.0f * a.flow_scale;
     p.cum_in = reinterpret_cast<const float2 *>(a.cum_in);
     p.cum_w = a.cum_w;
     p.cum_h_global = a.cum_h_global;
@@ -122,6 +123,10 @@ int launch_lk_level(const LkLevelArgs &a, cudaStream_t stream, unsigned long lon
     if (a.w < 1 || a.h_local < 1 || a.n_pairs < 1 || a.out_y0 < 0 || a.out_y1 > a.h_local || a.out_y0 >= a.out_y1) {
         set_error("lk_level: bad geometry (w %d h_local %d pairs %d out rows [%d,%d))", a.w, a.h_local, a.n_pairs,
                   a.out_y0, a.out_y1);
+        return OFB_ERR_INVALID;
+    }
+    if (a.pitch * (size_t)a.h_local > 0x7fffffffull || (size_t)a.w * a.h_local > 0x3fffffffull) {
+        set_error("lk_level: one image is limited to 2^31 bytes (pitch %zu x %d rows)", a.pitch, a.h_local);
         return OFB_ERR_INVALID;
     }
     if (a.n_pairs > 65535) {

@@ -5,6 +5,7 @@
 #include <cstdio>
 #include <cstring>
 #include <new>
+#include <vector>
 
 namespace ofb {
 
@@ -32,6 +33,14 @@ struct ofb_ctx {
     uint8_t *ws = nullptr;
     size_t ws_bytes = 0;
     unsigned long long launches = 0;
+    // optional in-situ timing: CUDA events around each fused-LK launch (tag = level) and around the
+    // pyramid build (tag = OFB_PROFILE_PYRAMID), recorded on the stream the work is launched on
+    struct ProfRec {
+        int tag;
+        cudaEvent_t a, b;
+    };
+    bool prof_on = false;
+    std::vector<ProfRec> prof;
 };
 
 namespace ofb {
@@ -145,6 +154,23 @@ static void plan_pairs(const ofb_params *p, PairPlan *pl, Carver *cv)
     pl->bytes = cv->off;
 }
 
+static int prof_begin(ofb_ctx *c, int tag, cudaStream_t st)
+{
+    if (!c->prof_on) return OFB_OK;
+    ofb_ctx::ProfRec r{tag, nullptr, nullptr};
+    OFB_CUDA_TRY(cudaEventCreate(&r.a));
+    OFB_CUDA_TRY(cudaEventCreate(&r.b));
+    OFB_CUDA_TRY(cudaEventRecord(r.a, st));
+    c->prof.push_back(r);
+    return OFB_OK;
+}
+static int prof_end(ofb_ctx *c, cudaStream_t st)
+{
+    if (!c->prof_on || c->prof.empty()) return OFB_OK;
+    OFB_CUDA_TRY(cudaEventRecord(c->prof.back().b, st));
+    return OFB_OK;
+}
+
 static int run_pairs_device(ofb_ctx *c, const ofb_params *p, const PairPlan &pl, uint8_t *base, const uint8_t *prev0,
                             const uint8_t *next0, size_t pitch0, size_t istride0, float *const *flow_levels,
                             float *total_flow, cudaStream_t st)
@@ -156,6 +182,10 @@ static int run_pairs_device(ofb_ctx *c, const ofb_params *p, const PairPlan &pl,
     pn[0] = next0;
     pitch[0] = pitch0;
     istr[0] = istride0;
+    if (L > 1) {
+        int rc = prof_begin(c, OFB_PROFILE_PYRAMID, st);
+        if (rc) return rc;
+    }
     for (int k = 1; k < L; k++) {
         pp[k] = base + pl.off_prev[k];
         pn[k] = base + pl.off_next[k];
@@ -166,6 +196,10 @@ static int run_pairs_device(ofb_ctx *c, const ofb_params *p, const PairPlan &pl,
         if (rc) return rc;
         rc = launch_pyr_down(pn[k - 1], pitch[k - 1], istr[k - 1], pl.w[k - 1], pl.h[k - 1], const_cast<uint8_t *>(pn[k]),
                              pitch[k], istr[k], n, 1, st, &c->launches);
+        if (rc) return rc;
+    }
+    if (L > 1) {
+        int rc = prof_end(c, st);
         if (rc) return rc;
     }
     for (int k = L - 1; k >= 0; k--) {
@@ -198,7 +232,11 @@ static int run_pairs_device(ofb_ctx *c, const ofb_params *p, const PairPlan &pl,
         }
         if (k == 0) a.cum_out = total_flow;
         else if (k <= L - 2) a.cum_out = reinterpret_cast<float *>(base + pl.off_cum[k]);
-        int rc = launch_lk_level(a, st, &c->launches);
+        int rc = prof_begin(c, k, st);
+        if (rc) return rc;
+        rc = launch_lk_level(a, st, &c->launches);
+        if (rc) return rc;
+        rc = prof_end(c, st);
         if (rc) return rc;
     }
     return OFB_OK;
@@ -275,6 +313,10 @@ int ofb_ctx_destroy(ofb_ctx *c)
         DeviceGuard g(c->device);
         if (g.ok) {
             cudaDeviceSynchronize();
+            for (auto &r : c->prof) {
+                cudaEventDestroy(r.a);
+                cudaEventDestroy(r.b);
+            }
             if (c->ws) cudaFree(c->ws);
             if (c->stream) cudaStreamDestroy(c->stream);
         }
@@ -301,6 +343,38 @@ int ofb_ctx_launch_count(const ofb_ctx *c, unsigned long long *count)
 {
     OFB_CHECK_CTX(c);
     if (count) *count = c->launches;
+    return OFB_OK;
+}
+
+int ofb_ctx_profile_enable(ofb_ctx *c, int on)
+{
+    OFB_CHECK_CTX(c);
+    OFB_GUARD(c);
+    c->prof_on = on != 0;
+    for (auto &r : c->prof) {
+        cudaEventDestroy(r.a);
+        cudaEventDestroy(r.b);
+    }
+    c->prof.clear();
+    return OFB_OK;
+}
+
+int ofb_ctx_profile_read(ofb_ctx *c, int tag, double *ms_sum, unsigned long long *n_records)
+{
+    OFB_CHECK_CTX(c);
+    OFB_GUARD(c);
+    double sum = 0.0;
+    unsigned long long n = 0;
+    for (auto &r : c->prof) {
+        if (r.tag != tag) continue;
+        OFB_CUDA_TRY(cudaEventSynchronize(r.b));
+        float ms = 0.0f;
+        OFB_CUDA_TRY(cudaEventElapsedTime(&ms, r.a, r.b));
+        sum += ms;
+        n++;
+    }
+    if (ms_sum) *ms_sum = sum;
+    if (n_records) *n_records = n;
     return OFB_OK;
 }
 

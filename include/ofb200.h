@@ -161,6 +161,14 @@ int ofb_host_free(void *ptr);
 /* Number of kernels this library has launched on this context since creation (bench bookkeeping). */
 int ofb_ctx_launch_count(const ofb_ctx *ctx, unsigned long long *count);
 
+/* In-situ kernel timing for the roofline report.  While enabled, ofb_flow_pairs_device/_host put a
+ * CUDA-event pair (on the stream the work is launched on) around every fused-LK launch, tagged with
+ * its pyramid level, and around the pyramid build, tagged OFB_PROFILE_PYRAMID.  _enable(on) also
+ * discards earlier records.  _read waits for the tagged events and returns their summed duration. */
+#define OFB_PROFILE_PYRAMID 100
+int ofb_ctx_profile_enable(ofb_ctx *ctx, int on);
+int ofb_ctx_profile_read(ofb_ctx *ctx, int tag, double *ms_sum, unsigned long long *n_records);
+
 #ifdef __cplusplus
 }
 #endif

@@ -208,9 +208,13 @@ void orc_solve_i64(const int64_t *sxx, const int64_t *syy, const int64_t *sxy, c
  *   NEAREST:    pos_k = (i>>off, j>>off), the indexing main.cu:141-143 uses (the intended one);
  *               indices are clamped to the level (only matters for odd sizes).
  *   BILINEAR:   same (u,v) as NEAREST, sampled bilinearly in 8.8 fixed point (new work asked for
- *               by BASELINE.json north_star; no reference counterpart):
- *                 fx = j + u, fy = i + v; skipped unless 0 <= fx <= w-1 and 0 <= fy <= h-1
- *                 wx = (int)((fx - floor fx)*256 + 0.5), same for wy, x1 = min(x0+1, w-1)
+ *               by BASELINE.json north_star; no reference counterpart).  The flow is rounded to
+ *               1/256 px once, so that every pixel of a 2x2 block (which shares one coarser flow
+ *               vector) has the same integer offset and the same two weights:
+ *                 skipped unless |u| < 32768 and |v| < 32768 (also rejects NaN)
+ *                 U = rint(u*256), V = rint(v*256)  (round half to even); X = j*256 + U, Y = i*256 + V
+ *                 skipped unless 0 <= X <= (w-1)*256 and 0 <= Y <= (h-1)*256
+ *                 x0 = X>>8, wx = X&255, x1 = min(x0+1, w-1), same for y
  *                 val = ((256-wy)*((256-wx)*p00 + wx*p01) + wy*((256-wx)*p10 + wx*p11) + 32768) >> 16
  * Skipped pixels keep the unwarped next pixel.  (The reference pre-fills with a memcpy of only
  * w*h of the 3*w*h bytes (:247), so there skipped pixels beyond the first third are
@@ -257,10 +261,11 @@ void orc_warp_u8(const uint8_t *next, int W0, int H0, int level, int maxLevel, f
             }
             const float fx = (float)j + u, fy = (float)i + v;
             if (mode == ORC_WARP_BILINEAR) {
-                if (!(fx >= 0.0f && fx <= (float)(w - 1) && fy >= 0.0f && fy <= (float)(h - 1))) continue;
-                const int x0 = (int)fx, y0 = (int)fy;
-                const int wx = (int)((fx - (float)x0) * 256.0f + 0.5f);
-                const int wy = (int)((fy - (float)y0) * 256.0f + 0.5f);
+                if (!(fabsf(u) < 32768.0f && fabsf(v) < 32768.0f)) continue;
+                const int U = (int)rintf(u * 256.0f), V = (int)rintf(v * 256.0f);
+                const int X = j * 256 + U, Y = i * 256 + V;
+                if (X < 0 || X > (w - 1) * 256 || Y < 0 || Y > (h - 1) * 256) continue;
+                const int x0 = X >> 8, y0 = Y >> 8, wx = X & 255, wy = Y & 255;
                 const int x1 = x0 + 1 < w ? x0 + 1 : w - 1, y1 = y0 + 1 < h ? y0 + 1 : h - 1;
                 const int p00 = next[(size_t)y0 * w + x0], p01 = next[(size_t)y0 * w + x1];
                 const int p10 = next[(size_t)y1 * w + x0], p11 = next[(size_t)y1 * w + x1];
