@@ -214,6 +214,12 @@ class Context:
                                               C.c_void_p(stream)))
         return dst
 
+    def pyr_down_strip_device(self, src, sw: int, src_y_off: int, dst, dst_y0: int, dst_y1: int, stream: int = 0):
+        """Row-strip pyramid step: src (rows, pitch) holds global rows from src_y_off; dst (dst_y1-dst_y0, pitch_d)."""
+        L.check(self._lib.ofb_pyr_down_strip_device(self._h, src.data_ptr(), src.stride(0), sw, src.shape[0], src_y_off,
+                                                    dst.data_ptr(), dst.stride(0), dst_y0, dst_y1, C.c_void_p(stream)))
+        return dst
+
     def lk_level_device(self, prev, next, w: int, win: int, warp_mode: int = WARP_BILINEAR, flow_scale: float = 1.0,
                         cum_in=None, flow_out=None, cum_out=None, stream: int = 0):
         """One fused LK level on (n, h, pitch) uint8 tensors; cum_in is the (n, h>>1, w>>1, 2) cumulative

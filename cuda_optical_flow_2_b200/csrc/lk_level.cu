@@ -69,14 +69,26 @@ static int launch_one(const LkLevelArgs &a, cudaStream_t stream, unsigned long l
 
     const int out_rows = a.out_y1 - a.out_y0;
     const int strips = (a.w + C::TWO - 1) / C::TWO;
-    // enough CTAs for ~4 per SM, but never fewer rows per CTA than one chunk
-    const long long target = 4LL * (a.sm_count > 0 ? a.sm_count : 148);
-    long long ny = (target + (long long)strips * a.n_pairs - 1) / ((long long)strips * a.n_pairs);
+    // Rows per CTA.  The hardware hands CTAs to SMs as slots free up, so a launch takes about
+    // (total row-steps) / SMs plus a ragged tail of roughly half a CTA's lifetime (MIN_BLOCKS CTAs
+    // share an SM, so a CTA lives MIN_BLOCKS times its own row-steps).  Short CTAs shrink the tail,
+    // tall CTAs amortise the 2R+2 halo rows: take the split that minimises the sum.
+    const int n_sm = a.sm_count > 0 ? a.sm_count : 148;
+    const long long cols = (long long)strips * a.n_pairs;
     const int max_ny = (out_rows + C::CH - 1) / C::CH;
-    if (ny > max_ny) ny = max_ny;
-    if (ny < 1) ny = 1;
-    int rows_per_block = (int)((out_rows + ny - 1) / ny);
-    rows_per_block = ((rows_per_block + C::CH - 1) / C::CH) * C::CH;
+    int rows_per_block = out_rows;
+    double best = 1e300;
+    for (int ny = 1; ny <= max_ny && ny <= 128; ny++) {
+        int rpb = (out_rows + ny - 1) / ny;
+        rpb = ((rpb + C::SUB - 1) / C::SUB) * C::SUB;
+        const int nb = (out_rows + rpb - 1) / rpb;
+        const double steps = rpb + 2 * C::R + 2 + C::SUB;
+        const double cost = (double)(cols * nb) * steps / n_sm + 0.5 * C::MIN_BLOCKS * steps;
+        if (cost < best * 0.999) {
+            best = cost;
+            rows_per_block = rpb;
+        }
+    }
     const int nby = (out_rows + rows_per_block - 1) / rows_per_block;
 
     LkKernelParams p;

@@ -445,6 +445,19 @@ int ofb_pyr_down_device(ofb_ctx *c, const uint8_t *src_d, size_t src_pitch, size
                            static_cast<cudaStream_t>(stream), &c->launches);
 }
 
+int ofb_pyr_down_strip_device(ofb_ctx *c, const uint8_t *src_d, size_t src_pitch, int sw, int src_rows, int src_y_off,
+                              uint8_t *dst_d, size_t dst_pitch, int dst_y0, int dst_y1, void *stream)
+{
+    OFB_CHECK_CTX(c);
+    if (!src_d || !dst_d) {
+        set_error("NULL image pointer");
+        return OFB_ERR_INVALID;
+    }
+    OFB_GUARD(c);
+    return launch_pyr_down_strip(src_d, src_pitch, sw, src_rows, src_y_off, dst_d, dst_pitch, dst_y0, dst_y1,
+                                 static_cast<cudaStream_t>(stream), &c->launches);
+}
+
 int ofb_lk_level_device(ofb_ctx *c, const uint8_t *prev_d, const uint8_t *next_d, size_t pitch_bytes,
                         size_t image_stride_bytes, int w, int h, int n_pairs, int win, int warp_mode, float flow_scale,
                         const float *cum_in_d, float *flow_out_d, float *cum_out_d, void *stream)

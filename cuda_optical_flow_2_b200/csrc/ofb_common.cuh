@@ -53,6 +53,9 @@ int launch_pyr_down(const uint8_t *src, size_t src_pitch, size_t src_stride, int
                     size_t dst_pitch, size_t dst_stride, int n_images, int channels, cudaStream_t stream,
                     unsigned long long *launches);
 
+int launch_pyr_down_strip(const uint8_t *src, size_t src_pitch, int sw, int src_rows, int src_y_off, uint8_t *dst,
+                          size_t dst_pitch, int dst_y0, int dst_y1, cudaStream_t stream, unsigned long long *launches);
+
 // ---- stage kernels + layout helpers (stages.cu) --------------------------------------------
 int launch_c3_to_planar(const uint8_t *src_c3, int w, int h, int n_images, uint8_t *dst, size_t dst_pitch,
                         size_t dst_stride, cudaStream_t stream, unsigned long long *launches);

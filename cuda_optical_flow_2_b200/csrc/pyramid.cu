@@ -10,8 +10,9 @@ namespace ofb {
 // Planar u8, four outputs per thread: 3 rows x (1 + 8) source bytes, one 32-bit store.
 __global__ void __launch_bounds__(256)
 pyr_down_planar_kernel(const uint8_t *__restrict__ src, size_t src_pitch, size_t src_stride, int dw, int dh,
-                       uint8_t *__restrict__ dst, size_t dst_pitch, size_t dst_stride)
+                       uint8_t *__restrict__ dst, size_t dst_pitch, size_t dst_stride, int src_y_off, int dst_y0)
 {
+    // Row strips: dst local row y is global row dst_y0 + y; src local row 0 is global row src_y_off.
     const int x0 = 4 * (blockIdx.x * 32 + threadIdx.x);
     const int y = blockIdx.y * 8 + threadIdx.y;
     if (x0 >= dw || y >= dh) return;
@@ -21,8 +22,9 @@ pyr_down_planar_kernel(const uint8_t *__restrict__ src, size_t src_pitch, size_t
     int acc[4] = {0, 0, 0, 0};
 #pragma unroll
     for (int r = 0; r < 3; r++) {
-        const int sy = 2 * y - 1 + r;
-        if (sy < 0) continue;
+        const int sg = 2 * (dst_y0 + y) - 1 + r; // global source row; above the image: skipped
+        if (sg < 0) continue;
+        const int sy = sg - src_y_off;
         const uint8_t *row = s + (size_t)sy * src_pitch + 2 * x0;
         int v[9];
         v[0] = (x0 > 0) ? (int)__ldg(row - 1) : 0;
@@ -80,6 +82,29 @@ pyr_down_interleaved_kernel(const uint8_t *__restrict__ src, size_t src_pitch, i
     dst[(size_t)y * dst_pitch + xb] = (uint8_t)(acc >> 4);
 }
 
+int launch_pyr_down_strip(const uint8_t *src, size_t src_pitch, int sw, int src_rows, int src_y_off, uint8_t *dst,
+                          size_t dst_pitch, int dst_y0, int dst_y1, cudaStream_t stream, unsigned long long *launches)
+{
+    const int dw = sw >> 1, dh = dst_y1 - dst_y0;
+    // rows 2*y-1 .. 2*y+1 of every destination row must be in the source strip (or above the image)
+    const int first = 2 * dst_y0 - 1 < 0 ? 0 : 2 * dst_y0 - 1, last = 2 * (dst_y1 - 1) + 1;
+    if (dw < 1 || dh < 1 || first < src_y_off || last >= src_y_off + src_rows) {
+        set_error("pyr_down_strip: destination rows [%d,%d) need source rows [%d,%d], strip holds [%d,%d)", dst_y0, dst_y1,
+                  first, last, src_y_off, src_y_off + src_rows);
+        return OFB_ERR_INVALID;
+    }
+    if ((src_pitch & 7) || (dst_pitch & 3) || (reinterpret_cast<uintptr_t>(src) & 7) || (reinterpret_cast<uintptr_t>(dst) & 3)) {
+        set_error("pyr_down_strip: planar images need 8-byte aligned source rows and 4-byte aligned destination rows");
+        return OFB_ERR_INVALID;
+    }
+    dim3 block(32, 8);
+    dim3 grid((unsigned)((dw + 127) / 128), (unsigned)((dh + 7) / 8), 1);
+    pyr_down_planar_kernel<<<grid, block, 0, stream>>>(src, src_pitch, 0, dw, dh, dst, dst_pitch, 0, src_y_off, dst_y0);
+    OFB_CUDA_TRY(cudaGetLastError());
+    if (launches) ++*launches;
+    return OFB_OK;
+}
+
 int launch_pyr_down(const uint8_t *src, size_t src_pitch, size_t src_stride, int sw, int sh, uint8_t *dst,
                     size_t dst_pitch, size_t dst_stride, int n_images, int channels, cudaStream_t stream,
                     unsigned long long *launches)
@@ -101,7 +126,7 @@ int launch_pyr_down(const uint8_t *src, size_t src_pitch, size_t src_stride, int
         }
         dim3 block(32, 8);
         dim3 grid((unsigned)((dw + 127) / 128), (unsigned)((dh + 7) / 8), (unsigned)n_images);
-        pyr_down_planar_kernel<<<grid, block, 0, stream>>>(src, src_pitch, src_stride, dw, dh, dst, dst_pitch, dst_stride);
+        pyr_down_planar_kernel<<<grid, block, 0, stream>>>(src, src_pitch, src_stride, dw, dh, dst, dst_pitch, dst_stride, 0, 0);
         OFB_CUDA_TRY(cudaGetLastError());
         if (launches) ++*launches;
     } else {

@@ -85,6 +85,13 @@ int ofb_flow_pairs_device(ofb_ctx *ctx, const ofb_params *p, const uint8_t *prev
 int ofb_pyr_down_device(ofb_ctx *ctx, const uint8_t *src_d, size_t src_pitch, size_t src_image_stride, int sw, int sh,
                         uint8_t *dst_d, size_t dst_pitch, size_t dst_image_stride, int n_images, void *stream);
 
+/* Row-strip variant of ofb_pyr_down_device for frames partitioned across GPUs: the source buffer
+ * holds global rows [src_y_off, src_y_off + src_rows) of a level of width sw; destination rows
+ * [dst_y0, dst_y1) (global numbering) of the next level are written to dst_d, whose row 0 is
+ * global row dst_y0.  Source rows 2y-1 .. 2y+1 must be present for every destination row y. */
+int ofb_pyr_down_strip_device(ofb_ctx *ctx, const uint8_t *src_d, size_t src_pitch, int sw, int src_rows,
+                              int src_y_off, uint8_t *dst_d, size_t dst_pitch, int dst_y0, int dst_y1, void *stream);
+
 /* One fused LK level on device-resident planar images: warp next by the coarser cumulative flow,
  * Ix/Iy/It, five window sums, solve.  Replaces the body of gpu::calc_opt_flow for one level
  * (OptFlowGpu.cu:1909-1979) without its host round trips.

@@ -1,0 +1,164 @@
+"""Multi-GPU host logic.  CPU: strip schedule invariants and a world_size-2 gloo run of the halo
+exchange.  GPU: N emulated ranks on one device must reproduce the whole-frame flow bit for bit."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_shard_range_partitions_the_batch():
+    from cuda_optical_flow_2_b200.dist import shard_range
+
+    for n, world in ((4096, 8), (10, 4), (3, 8), (0, 2)):
+        blocks = [shard_range(n, world, r) for r in range(world)]
+        assert blocks[0][0] == 0 and blocks[-1][1] == n
+        assert all(a[1] == b[0] for a, b in zip(blocks, blocks[1:]))
+        sizes = [hi - lo for lo, hi in blocks]
+        assert max(sizes) - min(sizes) <= 1
+
+
+@pytest.mark.parametrize("W,H,levels,win,world", [(7680, 4320, 4, 9, 8), (7680, 4320, 4, 9, 2), (3840, 2160, 4, 15, 4),
+                                                  (640, 486, 3, 5, 3), (1920, 1080, 3, 9, 8)])
+def test_strip_plan_invariants(W, H, levels, win, world):
+    from cuda_optical_flow_2_b200.dist import StripPlan
+
+    plan = StripPlan(W, H, levels, win, world, reach=8)
+    plan.validate()
+    r = win // 2
+    for k in range(levels):
+        for rk in range(world):
+            s = plan.level(k, rk)
+            # strips nest: a rank's rows at level k sit on its rows at level k+1
+            if k + 1 < levels:
+                up = plan.level(k + 1, rk)
+                assert s.y0 == 2 * up.y0 and (s.y1 == 2 * up.y1 or rk == world - 1)
+                # pyramid: level k+1 own rows need level k rows 2y-1 .. 2y+1, all inside the level-k buffer
+                assert s.by0 <= max(0, 2 * up.y0 - 1) and 2 * (up.y1 - 1) + 1 < s.by1
+                # the kernel looks up cum[(y >> 1)] for the rows of its tile
+                lo, hi = max(0, s.y0 - r - 2), min(s.h - 1, s.y1 + r + 1)
+                assert s.cy0 <= lo >> 1 and min(hi >> 1, (H >> (k + 1)) - 1) < s.cy1
+            # stencil + window halo present (or the image border)
+            assert s.by0 <= max(0, s.y0 - r - 2) and s.by1 >= min(s.h, s.y1 + r + 2)
+            # every halo row is owned by exactly one sender
+            got = np.zeros(s.h, int)
+            got[s.y0:s.y1] += 1
+            for peer in range(world):
+                for dst, lo, hi, _ in plan.halo_messages(k, peer):
+                    if dst == rk:
+                        got[lo:hi] += 1
+            assert (got[s.by0:s.by1] == 1).all() and got.sum() == s.buf_rows
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _gloo_worker(rank, world, port, q):
+    """Each rank fills its own rows with a global-row pattern; after the exchange its buffer (own rows
+    + halo) must equal the pattern of the whole image, for images and for the coarser flow."""
+    sys.path.insert(0, ROOT)
+    import torch
+    import torch.distributed as dist
+
+    from cuda_optical_flow_2_b200.dist import DistTransport, StripPlan, StripRunner
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        W, H, levels, win = 96, 160, 3, 5
+        plan = StripPlan(W, H, levels, win, world, reach=4)
+        rn = StripRunner(None, plan, rank, DistTransport(), torch.device("cpu"))
+        ok = True
+        for k in range(levels):
+            s = rn.strips[k]
+            rows = torch.arange(s.by0, s.by1)
+            own = (rows >= s.y0) & (rows < s.y1)
+            pat_p = ((rows[:, None] * 7 + torch.arange(rn.pitch[k])[None, :] * 3 + k) % 251).to(torch.uint8)
+            pat_n = ((rows[:, None] * 5 + torch.arange(rn.pitch[k])[None, :] * 11 + k) % 241).to(torch.uint8)
+            rn.prev[k][own] = pat_p[own]
+            rn.next[k][own] = pat_n[own]
+            rn._run(rn.image_exchange(k))
+            ok &= bool(torch.equal(rn.prev[k], pat_p) and torch.equal(rn.next[k], pat_n))
+        for k in range(levels - 2, -1, -1):
+            s, up = rn.strips[k], rn.strips[k + 1]
+            src = rn.cum[k + 1] if k + 1 < levels - 1 else rn.flow[k + 1]
+            rows = torch.arange(up.by0, up.by1, dtype=torch.float32)
+            own = (rows >= up.y0) & (rows < up.y1)
+            pat = rows[:, None, None] * 1000 + torch.arange(up.w, dtype=torch.float32)[None, :, None] + \
+                torch.tensor([0.25, 0.5])[None, None, :]
+            src[own] = pat[own]
+            rn._run(rn.cum_exchange(k))
+            crow = torch.arange(s.cy0, s.cy1, dtype=torch.float32)
+            exp = crow[:, None, None] * 1000 + torch.arange(up.w, dtype=torch.float32)[None, :, None] + \
+                torch.tensor([0.25, 0.5])[None, None, :]
+            ok &= bool(torch.equal(rn.cum_in[k][: s.cy1 - s.cy0], exp))
+        q.put((rank, ok))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_halo_exchange_over_gloo(world):
+    import torch.multiprocessing as mp
+
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_gloo_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert sorted(results) == [(r, True) for r in range(world)]
+
+
+# ------------------------------------------------------------------------------------------------- GPU
+@pytest.mark.gpu
+@pytest.mark.parametrize("W,H,levels,win,world,mode", [(640, 480, 3, 9, 2, 2), (640, 480, 3, 9, 4, 2), (322, 406, 2, 5, 3, 2),
+                                                       (640, 480, 3, 9, 3, 1), (1920, 1080, 3, 9, 8, 2),
+                                                       (512, 384, 1, 9, 4, 2)])
+def test_strips_reproduce_whole_frame_bit_for_bit(ctx, oracle, W, H, levels, win, world, mode):
+    import torch
+
+    from cuda_optical_flow_2_b200 import planar_to_device
+    from cuda_optical_flow_2_b200.dist import run_strips_local_w
+
+    prev = oracle.make_frame(W, H, 0, 0, 8, 77)
+    nxt = oracle.make_frame(W, H, 2.0, -1.5, 8, 77)
+    dp, dn = planar_to_device(prev[None]), planar_to_device(nxt[None])
+    total = torch.empty((1, H, W, 2), dtype=torch.float32, device="cuda")
+    whole = ctx.flow_pairs_device(dp, dn, W, levels, win, warp_mode=mode, total_flow=total)
+    plan, runners = run_strips_local_w(ctx, dp[0], dn[0], W, levels, win, world, warp_mode=mode, reach=16)
+    torch.cuda.synchronize()
+    for k in range(levels):
+        got = torch.cat([rn.own_flow(k) for rn in runners]).cpu().numpy()
+        ref = whole[k][0].cpu().numpy()
+        assert got.shape == ref.shape
+        assert np.array_equal(np.isnan(got), np.isnan(ref)), f"level {k}"
+        m = ~np.isnan(ref)
+        assert np.array_equal(got[m], ref[m]), f"level {k}: strips differ from the whole-frame result"
+    got = torch.cat([rn.own_total_flow() for rn in runners]).cpu().numpy()
+    ref = total[0].cpu().numpy()
+    m = ~np.isnan(ref)
+    assert np.array_equal(got[m], ref[m]), "total flow"
+
+
+@pytest.mark.gpu
+def test_strip_reach_overflow_is_reported(ctx, oracle):
+    """A warp that reaches past the exchanged rows must raise, not silently change the numbers."""
+    from cuda_optical_flow_2_b200 import planar_to_device
+    from cuda_optical_flow_2_b200.dist import run_strips_local_w
+
+    W, H = 320, 480
+    prev = oracle.make_frame(W, H, 0, 0, 8, 5)
+    nxt = oracle.make_frame(W, H, 0.0, 14.0, 8, 5)  # large vertical motion
+    with pytest.raises(RuntimeError, match="reach"):
+        run_strips_local_w(ctx, planar_to_device(prev[None])[0], planar_to_device(nxt[None])[0], W, 3, 9, 4, reach=1)
