@@ -23,6 +23,8 @@ static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; 
 
 } // namespace ofb
 
+#define OFB_LANES 2
+
 // One growable device workspace per context; carved by offset for each call.  Growing it frees the
 // old block (cudaFree synchronises the device), so steady-state calls allocate nothing -- unlike
 // the reference, which does 30 cudaMalloc/cudaFree pairs per level (OptFlowGpu.cu:1105-1124 etc.).
@@ -30,6 +32,7 @@ struct ofb_ctx {
     int device = 0;
     int sm_count = 0;
     cudaStream_t stream = nullptr; // used by the synchronous host-pointer entry points
+    cudaStream_t lane_stream[OFB_LANES] = {}; // the batched host entry point pipelines sub-batches over these
     uint8_t *ws = nullptr;
     size_t ws_bytes = 0;
     unsigned long long launches = 0;
@@ -302,6 +305,14 @@ int ofb_ctx_create(int device, ofb_ctx **out)
         delete c;
         return OFB_ERR_CUDA;
     }
+    for (int l = 0; l < OFB_LANES; l++) {
+        e = cudaStreamCreateWithFlags(&c->lane_stream[l], cudaStreamNonBlocking);
+        if (e != cudaSuccess) {
+            set_error("cudaStreamCreate failed: %s", cudaGetErrorString(e));
+            delete c;
+            return OFB_ERR_CUDA;
+        }
+    }
     *out = c;
     return OFB_OK;
 }
@@ -319,6 +330,8 @@ int ofb_ctx_destroy(ofb_ctx *c)
             }
             if (c->ws) cudaFree(c->ws);
             if (c->stream) cudaStreamDestroy(c->stream);
+            for (int l = 0; l < OFB_LANES; l++)
+                if (c->lane_stream[l]) cudaStreamDestroy(c->lane_stream[l]);
         }
     }
     delete c;
@@ -776,43 +789,63 @@ int ofb_flow_pairs_host(ofb_ctx *c, const ofb_params *p, const unsigned char *pr
             return OFB_ERR_INVALID;
         }
     OFB_GUARD(c);
+    // Software pipeline over sub-batches on OFB_LANES streams: while one lane downloads its flow the
+    // other uploads and computes, so the PCIe directions and the SMs overlap (with pinned host memory).
     const int n = p->n_pairs;
+    int sub = n / (2 * OFB_LANES);
+    if (sub < 1) sub = 1;
+    if (sub > 8) sub = 8;
+    ofb_params ps = *p;
+    ps.n_pairs = sub;
     const size_t pitch0 = align_up((size_t)p->w, 64), istride0 = pitch0 * (size_t)p->h;
-    Carver cv;
-    const size_t off_p0 = cv.take(istride0 * n), off_n0 = cv.take(istride0 * n);
     const size_t c3 = (size_t)p->w * p->h * 3;
-    const size_t off_c3 = (channels == 3) ? cv.take(c3 * n * 2) : 0;
-    size_t off_flow[OFB_MAX_LEVELS];
-    for (int k = 0; k < p->levels; k++) off_flow[k] = cv.take((size_t)(p->w >> k) * (p->h >> k) * 8 * n);
+    size_t lane_bytes = 0;
+    size_t off_p0, off_n0, off_c3 = 0, off_flow[OFB_MAX_LEVELS], plan_base;
     PairPlan pl;
-    const size_t plan_base = cv.off;
-    Carver cv2;
-    plan_pairs(p, &pl, &cv2);
-    rc = ws_reserve(c, plan_base + pl.bytes);
-    if (rc) return rc;
-    cudaStream_t st = c->stream;
-    uint8_t *B = c->ws;
-    if (channels == 1) {
-        OFB_CUDA_TRY(cudaMemcpy2DAsync(B + off_p0, pitch0, prev_h, (size_t)p->w, (size_t)p->w, (size_t)p->h * n,
-                                       cudaMemcpyHostToDevice, st));
-        OFB_CUDA_TRY(cudaMemcpy2DAsync(B + off_n0, pitch0, next_h, (size_t)p->w, (size_t)p->w, (size_t)p->h * n,
-                                       cudaMemcpyHostToDevice, st));
-    } else {
-        OFB_CUDA_TRY(cudaMemcpyAsync(B + off_c3, prev_h, c3 * n, cudaMemcpyHostToDevice, st));
-        OFB_CUDA_TRY(cudaMemcpyAsync(B + off_c3 + c3 * n, next_h, c3 * n, cudaMemcpyHostToDevice, st));
-        rc = launch_c3_to_planar(B + off_c3, p->w, p->h, n, B + off_p0, pitch0, istride0, st, &c->launches);
-        if (rc) return rc;
-        rc = launch_c3_to_planar(B + off_c3 + c3 * n, p->w, p->h, n, B + off_n0, pitch0, istride0, st, &c->launches);
-        if (rc) return rc;
+    {
+        Carver cv;
+        off_p0 = cv.take(istride0 * sub);
+        off_n0 = cv.take(istride0 * sub);
+        if (channels == 3) off_c3 = cv.take(c3 * sub * 2);
+        for (int k = 0; k < p->levels; k++) off_flow[k] = cv.take((size_t)(p->w >> k) * (p->h >> k) * 8 * sub);
+        plan_base = cv.off;
+        Carver cv2;
+        plan_pairs(&ps, &pl, &cv2);
+        lane_bytes = align_up(plan_base + pl.bytes, 256);
     }
-    float *flow_d[OFB_MAX_LEVELS];
-    for (int k = 0; k < p->levels; k++) flow_d[k] = reinterpret_cast<float *>(B + off_flow[k]);
-    rc = run_pairs_device(c, p, pl, B + plan_base, B + off_p0, B + off_n0, pitch0, istride0, flow_d, nullptr, st);
+    rc = ws_reserve(c, lane_bytes * OFB_LANES);
     if (rc) return rc;
-    for (int k = p->levels - 1; k >= 0; k--)
-        OFB_CUDA_TRY(cudaMemcpyAsync(flow_levels_h[k], flow_d[k], (size_t)(p->w >> k) * (p->h >> k) * 8 * n,
-                                     cudaMemcpyDeviceToHost, st));
-    OFB_CUDA_TRY(cudaStreamSynchronize(st));
+    for (int first = 0, sb = 0; first < n; first += sub, sb++) {
+        const int lane = sb % OFB_LANES;
+        const int cnt = (n - first < sub) ? n - first : sub;
+        cudaStream_t st = c->lane_stream[lane];
+        uint8_t *B = c->ws + lane_bytes * lane;
+        ofb_params pc = *p;
+        pc.n_pairs = cnt;
+        if (channels == 1) {
+            OFB_CUDA_TRY(cudaMemcpy2DAsync(B + off_p0, pitch0, prev_h + (size_t)first * p->w * p->h, (size_t)p->w, (size_t)p->w,
+                                           (size_t)p->h * cnt, cudaMemcpyHostToDevice, st));
+            OFB_CUDA_TRY(cudaMemcpy2DAsync(B + off_n0, pitch0, next_h + (size_t)first * p->w * p->h, (size_t)p->w, (size_t)p->w,
+                                           (size_t)p->h * cnt, cudaMemcpyHostToDevice, st));
+        } else {
+            OFB_CUDA_TRY(cudaMemcpyAsync(B + off_c3, prev_h + c3 * first, c3 * cnt, cudaMemcpyHostToDevice, st));
+            OFB_CUDA_TRY(cudaMemcpyAsync(B + off_c3 + c3 * sub, next_h + c3 * first, c3 * cnt, cudaMemcpyHostToDevice, st));
+            rc = launch_c3_to_planar(B + off_c3, p->w, p->h, cnt, B + off_p0, pitch0, istride0, st, &c->launches);
+            if (rc) return rc;
+            rc = launch_c3_to_planar(B + off_c3 + c3 * sub, p->w, p->h, cnt, B + off_n0, pitch0, istride0, st, &c->launches);
+            if (rc) return rc;
+        }
+        float *flow_d[OFB_MAX_LEVELS];
+        for (int k = 0; k < p->levels; k++) flow_d[k] = reinterpret_cast<float *>(B + off_flow[k]);
+        rc = run_pairs_device(c, &pc, pl, B + plan_base, B + off_p0, B + off_n0, pitch0, istride0, flow_d, nullptr, st);
+        if (rc) return rc;
+        for (int k = p->levels - 1; k >= 0; k--) {
+            const size_t per_pair = (size_t)(p->w >> k) * (p->h >> k) * 2; // floats
+            OFB_CUDA_TRY(cudaMemcpyAsync(flow_levels_h[k] + per_pair * first, flow_d[k], per_pair * 4 * cnt,
+                                         cudaMemcpyDeviceToHost, st));
+        }
+    }
+    for (int lane = 0; lane < OFB_LANES; lane++) OFB_CUDA_TRY(cudaStreamSynchronize(c->lane_stream[lane]));
     return OFB_OK;
 }
 
