@@ -162,3 +162,25 @@ def test_strip_reach_overflow_is_reported(ctx, oracle):
     nxt = oracle.make_frame(W, H, 0.0, 14.0, 8, 5)  # large vertical motion
     with pytest.raises(RuntimeError, match="reach"):
         run_strips_local_w(ctx, planar_to_device(prev[None])[0], planar_to_device(nxt[None])[0], W, 3, 9, 4, reach=1)
+
+
+@pytest.mark.gpu
+def test_config4_8k_strips_equal_whole_frame(ctx, oracle):
+    """configs[4]: 7680x4320 pair cut into 8 row strips (emulated ranks on one GPU)."""
+    import torch
+
+    from cuda_optical_flow_2_b200 import planar_to_device
+    from cuda_optical_flow_2_b200.dist import run_strips_local_w
+
+    W, H, levels, win = 7680, 4320, 4, 9
+    prev = oracle.make_frame(W, H, 0, 0, 16, 3)
+    nxt = oracle.make_frame(W, H, 6.0, 4.0, 16, 3)
+    dp, dn = planar_to_device(prev[None]), planar_to_device(nxt[None])
+    whole = ctx.flow_pairs_device(dp, dn, W, levels, win)
+    plan, runners = run_strips_local_w(ctx, dp[0], dn[0], W, levels, win, 8, reach=16)
+    torch.cuda.synchronize()
+    for k in range(levels):
+        got = torch.cat([rn.own_flow(k) for rn in runners])
+        ref = whole[k][0]
+        m = ~torch.isnan(ref)
+        assert torch.equal(torch.isnan(got), torch.isnan(ref)) and torch.equal(got[m], ref[m]), f"level {k}"

@@ -219,3 +219,97 @@ def test_flow_pairs_host(ctx, oracle):
         for k in range(levels):
             assert_flow_identical(got1[k][i], ref[k], f"planar pair {i} level {k}")
             assert_flow_identical(got3[k][i], ref[k], f"c3 pair {i} level {k}")
+
+
+# ------------------------------------------------------------------------------------ BASELINE.json configurations
+def test_config0_640x480_one_level_win5(ctx, oracle):
+    """configs[0]: single 640x480 pair, 1 level, 5x5 window (the case the reference CPU path runs)."""
+    torch = _torch()
+    from cuda_optical_flow_2_b200 import planar_to_device
+
+    prev, nxt = frames(oracle, 640, 480, 0.6, -0.4, 8)
+    flows = ctx.flow_pairs_device(planar_to_device(prev[None]), planar_to_device(nxt[None]), 640, 1, 5)
+    torch.cuda.synchronize()
+    assert_flow_identical(flows[0][0].cpu().numpy(), oracle.lk_level(prev, nxt, 5, oracle.SUMS_EXACT), "config 0")
+    assert_flow_close(flows[0][0].cpu().numpy(), oracle.lk_level(prev, nxt, 5, oracle.SUMS_F32_SEQUENTIAL), "config 0 vs fp32")
+
+
+def test_config2_4k_four_levels_win15(ctx, oracle):
+    """configs[2]: 3840x2160 pair, 4-level pyramid, 15x15 window."""
+    torch = _torch()
+    from cuda_optical_flow_2_b200 import planar_to_device
+
+    w, h, levels, win = 3840, 2160, 4, 15
+    prev, nxt = frames(oracle, w, h, 5.0, -3.0, 16)
+    flows = ctx.flow_pairs_device(planar_to_device(prev[None]), planar_to_device(nxt[None]), w, levels, win)
+    torch.cuda.synchronize()
+    ref = oracle.flow_pair(prev, nxt, levels, win, 2, oracle.SUMS_EXACT)
+    for k in range(levels):
+        assert_flow_identical(flows[k][0].cpu().numpy(), ref[k], f"4K level {k}")
+
+
+def test_config3_batch_equals_single_pairs(ctx, oracle):
+    """configs[3] property at a reduced count: every pair of a 1080p batch equals the same pair run alone
+    (pairs share nothing), and the batch does not depend on the batch size."""
+    torch = _torch()
+    from cuda_optical_flow_2_b200 import planar_to_device
+
+    w, h, levels, win, n = 1920, 1080, 3, 9, 6
+    prevs = np.stack([oracle.make_frame(w, h, 0, 0, 8, 40 + i) for i in range(n)])
+    nexts = np.stack([oracle.make_frame(w, h, 1.0 + i, 0.5 * i, 8, 40 + i) for i in range(n)])
+    dp, dn = planar_to_device(prevs), planar_to_device(nexts)
+    batch = [f.clone() for f in ctx.flow_pairs_device(dp, dn, w, levels, win)]
+    for i in (0, 3, 5):
+        single = ctx.flow_pairs_device(dp[i:i + 1].contiguous(), dn[i:i + 1].contiguous(), w, levels, win)
+        torch.cuda.synchronize()
+        for k in range(levels):
+            a, b = batch[k][i].cpu().numpy(), single[k][0].cpu().numpy()
+            assert np.array_equal(np.isnan(a), np.isnan(b)) and np.array_equal(a[~np.isnan(a)], b[~np.isnan(b)])
+    ref = oracle.flow_pair(prevs[5], nexts[5], levels, win, 2, oracle.SUMS_EXACT)
+    for k in range(levels):
+        assert_flow_identical(batch[k][5].cpu().numpy(), ref[k], f"batch pair 5 level {k}")
+
+
+def test_config4_8k_whole_frame_vs_oracle(ctx, oracle):
+    """configs[4] frame (7680x4320, 4 levels, window 9) on one GPU against the oracle; the row-strip
+    split of the same frame is checked against this whole-frame result in tests/test_dist.py."""
+    torch = _torch()
+    from cuda_optical_flow_2_b200 import planar_to_device
+
+    w, h, levels, win = 7680, 4320, 4, 9
+    prev, nxt = frames(oracle, w, h, 6.0, 4.0, 16)
+    flows = ctx.flow_pairs_device(planar_to_device(prev[None]), planar_to_device(nxt[None]), w, levels, win)
+    torch.cuda.synchronize()
+    ref = oracle.flow_pair(prev, nxt, levels, win, 2, oracle.SUMS_EXACT)
+    for k in range(levels):
+        assert_flow_identical(flows[k][0].cpu().numpy(), ref[k], f"8K level {k}")
+
+
+@pytest.mark.parametrize("w,h,levels,win", [(17, 9, 1, 3), (40, 33, 2, 5), (129, 65, 3, 9), (2, 2, 1, 3), (121, 240, 1, 19)])
+def test_small_and_ragged_sizes(ctx, oracle, w, h, levels, win):
+    torch = _torch()
+    from cuda_optical_flow_2_b200 import planar_to_device
+
+    prev, nxt = frames(oracle, w, h, 0.7, 0.3, 4)
+    flows = ctx.flow_pairs_device(planar_to_device(prev[None]), planar_to_device(nxt[None]), w, levels, win)
+    torch.cuda.synchronize()
+    ref = oracle.flow_pair(prev, nxt, levels, win, 2, oracle.SUMS_EXACT)
+    for k in range(levels):
+        assert_flow_identical(flows[k][0].cpu().numpy(), ref[k], f"{w}x{h} level {k}")
+
+
+def test_bad_arguments_are_rejected(ctx):
+    import torch
+
+    from cuda_optical_flow_2_b200 import OfbError
+
+    img = torch.zeros((1, 64, 64), dtype=torch.uint8, device="cuda")
+    with pytest.raises(OfbError):
+        ctx.flow_pairs_device(img, img, 64, 3, 8)  # even window
+    with pytest.raises(OfbError):
+        ctx.flow_pairs_device(img, img, 64, 7, 9)  # too many levels for 64x64
+    with pytest.raises(OfbError):
+        ctx.flow_pairs_device(img, img, 64, 2, 21)  # window too large
+    bad = torch.zeros((1, 64, 72), dtype=torch.uint8, device="cuda")
+    with pytest.raises(OfbError):
+        ctx.flow_pairs_device(bad, bad, 64, 1, 9)  # pitch not a multiple of 16
