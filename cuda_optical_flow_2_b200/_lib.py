@@ -64,6 +64,14 @@ SIGNATURES = {
     "ofb_inverse_matrix_f32_host": (C.c_int, [_vp, f32p, f32p, f32p, f32p, f32p, C.POINTER(f32p), C.c_int, C.c_int,
                                               C.c_int]),
     "ofb_flow_pairs_host": (C.c_int, [_vp, C.POINTER(OfbParams), u8p, u8p, C.c_int, C.POINTER(f32p)]),
+    "ofb_grayscale_avg_host_u8c3": (C.c_int, [_vp, u8p, u8p, C.c_int, C.c_int]),
+    "ofb_bilinear_filter_host_u8c3": (C.c_int, [_vp, u8p, u8p, u8p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double,
+                                                C.c_double]),
+    "ofb_bilateral_planar_device": (C.c_int, [_vp, _vp, _sz, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double,
+                                              _vp, _sz, _vp]),
+    "ofb_stream_create": (C.c_int, [_vp, C.POINTER(OfbParams), C.c_int, C.c_double, C.c_double, C.POINTER(_vp)]),
+    "ofb_stream_push_bgr_host": (C.c_int, [_vp, u8p, C.POINTER(f32p), f32p, i32p]),
+    "ofb_stream_destroy": (C.c_int, [_vp]),
     "ofb_host_alloc": (C.c_int, [C.POINTER(_vp), _sz]),
     "ofb_host_free": (C.c_int, [_vp]),
 }

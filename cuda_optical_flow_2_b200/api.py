@@ -152,6 +152,40 @@ class Context:
         ptrs = (L.f32p * (level + 1))(*[a.ctypes.data_as(L.f32p) for a in arrs])
         L.check(self._lib.ofb_inverse_matrix_f32_host(self._h, *[s.ctypes.data_as(L.f32p) for s in sums], ptrs, level, w, h))
 
+    def grayscale_avg(self, src: np.ndarray, h: int, w: int) -> np.ndarray:
+        """gpu::grayscale_avg(src, dest, h, w) (OptFlowGpu.cu:75; height before width like the reference)."""
+        if src.shape != (h, w, 3):
+            raise ValueError("src must be (h, w, 3) uint8")
+        dst = np.empty_like(src)
+        L.check(self._lib.ofb_grayscale_avg_host_u8c3(self._h, _u8(src).ctypes.data_as(L.u8p), dst.ctypes.data_as(L.u8p), h, w))
+        return dst
+
+    def bilinear_filter(self, src: np.ndarray, gray: np.ndarray, w: int, h: int, ww: int, wh: int, sigmaS: float,
+                        sigmaB: float) -> np.ndarray:
+        """gpu::bilinear_filter (OptFlowGpu.cu:2050): the bilateral pre-filter of main.cu:240."""
+        if src.shape != (h, w, 3) or gray.shape != (h, w, 3):
+            raise ValueError("src/gray must be (h, w, 3) uint8")
+        dst = np.empty_like(src)
+        L.check(self._lib.ofb_bilinear_filter_host_u8c3(self._h, _u8(src).ctypes.data_as(L.u8p), _u8(gray).ctypes.data_as(L.u8p),
+                                                        dst.ctypes.data_as(L.u8p), w, h, ww, wh, float(sigmaS), float(sigmaB)))
+        return dst
+
+    def bilateral_planar_device(self, gray, w: int, ww: int, sigmaS: float, sigmaB: float, dst=None, stream: int = 0):
+        """Bilateral filter of a planar (h, pitch) uint8 CUDA tensor (src == gray)."""
+        import torch
+
+        h, pitch = gray.shape
+        if dst is None:
+            dst = torch.zeros_like(gray)
+        L.check(self._lib.ofb_bilateral_planar_device(self._h, gray.data_ptr(), pitch, w, h, ww, ww, float(sigmaS), float(sigmaB),
+                                                      dst.data_ptr(), dst.stride(0), C.c_void_p(stream)))
+        return dst
+
+    def open_stream(self, w: int, h: int, levels: int, win: int, warp_mode: int = WARP_BILINEAR, flow_scale: float = 1.0,
+                    bil_win: int = 0, bil_sigma_s: float = 2.0, bil_sigma_b: float = 10.0) -> "FrameStream":
+        """Frame sequence in the role of main.cu:222-275 (defaults of main.cu:236-240 for the pre-filter)."""
+        return FrameStream(self, w, h, levels, win, warp_mode, flow_scale, bil_win, bil_sigma_s, bil_sigma_b)
+
     # ---------------------------------------------------------------- whole-pair host API
     def flow_pairs_host(self, prev: np.ndarray, next: np.ndarray, levels: int, win: int,
                         warp_mode: int = WARP_BILINEAR, flow_scale: float = 1.0,
@@ -247,6 +281,42 @@ class Context:
             flow_out.data_ptr(), cum_out.data_ptr() if cum_out is not None else None,
             overflow_flag.data_ptr() if overflow_flag is not None else None, C.c_void_p(stream)))
         return flow_out
+
+
+class FrameStream:
+    """ofb_stream: push BGR frames one by one; every push after the first returns the flow against the
+    previous frame, whose pyramid stays on the device."""
+
+    def __init__(self, ctx: Context, w, h, levels, win, warp_mode, flow_scale, bil_win, bil_sigma_s, bil_sigma_b):
+        self._ctx, self._lib = ctx, ctx._lib
+        self.w, self.h, self.levels = w, h, levels
+        p = OfbParams(w, h, levels, win, warp_mode, flow_scale, 1)
+        hnd = C.c_void_p()
+        L.check(self._lib.ofb_stream_create(ctx._h, C.byref(p), bil_win, float(bil_sigma_s), float(bil_sigma_b), C.byref(hnd)))
+        self._h = hnd
+
+    def push(self, frame_bgr: np.ndarray, want_total: bool = False):
+        """Returns None for the first frame, else (flows, total) with flows[k] of shape (h>>k, w>>k, 2)."""
+        if frame_bgr.shape != (self.h, self.w, 3):
+            raise ValueError("frame must be (h, w, 3) uint8")
+        flows = [np.empty((self.h >> k, self.w >> k, 2), np.float32) for k in range(self.levels)]
+        total = np.empty((self.h, self.w, 2), np.float32) if want_total else None
+        ptrs = (L.f32p * self.levels)(*[f.ctypes.data_as(L.f32p) for f in flows])
+        has = C.c_int(0)
+        L.check(self._lib.ofb_stream_push_bgr_host(self._h, _u8(frame_bgr).ctypes.data_as(L.u8p), ptrs,
+                                                   total.ctypes.data_as(L.f32p) if want_total else None, C.byref(has)))
+        return (flows, total) if has.value else None
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.ofb_stream_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def planar_to_device(imgs: np.ndarray, device="cuda:0"):

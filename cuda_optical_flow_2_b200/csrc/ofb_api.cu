@@ -42,6 +42,7 @@ struct ofb_ctx {
         int tag;
         cudaEvent_t a, b;
     };
+    double *bil_lut = nullptr; // range-weight table of the bilateral pre-filter (device)
     bool prof_on = false;
     std::vector<ProfRec> prof;
 };
@@ -329,6 +330,7 @@ int ofb_ctx_destroy(ofb_ctx *c)
                 cudaEventDestroy(r.b);
             }
             if (c->ws) cudaFree(c->ws);
+            if (c->bil_lut) cudaFree(c->bil_lut);
             if (c->stream) cudaStreamDestroy(c->stream);
             for (int l = 0; l < OFB_LANES; l++)
                 if (c->lane_stream[l]) cudaStreamDestroy(c->lane_stream[l]);
@@ -846,6 +848,238 @@ int ofb_flow_pairs_host(ofb_ctx *c, const ofb_params *p, const unsigned char *pr
         }
     }
     for (int lane = 0; lane < OFB_LANES; lane++) OFB_CUDA_TRY(cudaStreamSynchronize(c->lane_stream[lane]));
+    return OFB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// pre-processing and the frame loop
+// ---------------------------------------------------------------------------------------------
+int ofb_grayscale_avg_host_u8c3(ofb_ctx *c, const unsigned char *src_h, unsigned char *dest_h, int h, int w)
+{
+    OFB_CHECK_CTX(c);
+    if (!src_h || !dest_h || w < 1 || h < 1) {
+        set_error("grayscale_avg: bad arguments");
+        return OFB_ERR_INVALID;
+    }
+    OFB_GUARD(c);
+    const size_t n = (size_t)w * h * 3;
+    Carver cv;
+    const size_t os = cv.take(n), od = cv.take(n);
+    int rc = ws_reserve(c, cv.off);
+    if (rc) return rc;
+    cudaStream_t st = c->stream;
+    OFB_CUDA_TRY(cudaMemcpyAsync(c->ws + os, src_h, n, cudaMemcpyHostToDevice, st));
+    rc = launch_grayscale(c->ws + os, w, h, c->ws + od, nullptr, 0, st, &c->launches);
+    if (rc) return rc;
+    OFB_CUDA_TRY(cudaMemcpyAsync(dest_h, c->ws + od, n, cudaMemcpyDeviceToHost, st));
+    OFB_CUDA_TRY(cudaStreamSynchronize(st));
+    return OFB_OK;
+}
+
+int ofb_bilinear_filter_host_u8c3(ofb_ctx *c, const unsigned char *src, const unsigned char *gray, unsigned char *dest,
+                                  int w, int h, int ww, int wh, double sigmaS, double sigmaB)
+{
+    OFB_CHECK_CTX(c);
+    if (!src || !gray || !dest || w < 1 || h < 1) {
+        set_error("bilinear_filter: bad arguments");
+        return OFB_ERR_INVALID;
+    }
+    OFB_GUARD(c);
+    const size_t n = (size_t)w * h * 3;
+    Carver cv;
+    const size_t os = cv.take(n), og = cv.take(n), od = cv.take(n), ol = cv.take(256 * sizeof(double));
+    int rc = ws_reserve(c, cv.off);
+    if (rc) return rc;
+    cudaStream_t st = c->stream;
+    OFB_CUDA_TRY(cudaMemcpyAsync(c->ws + os, src, n, cudaMemcpyHostToDevice, st));
+    const uint8_t *gd = c->ws + os;
+    if (gray != src) {
+        OFB_CUDA_TRY(cudaMemcpyAsync(c->ws + og, gray, n, cudaMemcpyHostToDevice, st));
+        gd = c->ws + og;
+    }
+    rc = launch_bilateral(c->ws + os, gd, (size_t)w * 3, 3, w, h, ww, wh, sigmaS, sigmaB,
+                          reinterpret_cast<double *>(c->ws + ol), c->ws + od, (size_t)w * 3, st, &c->launches);
+    if (rc) return rc;
+    OFB_CUDA_TRY(cudaMemcpyAsync(dest, c->ws + od, n, cudaMemcpyDeviceToHost, st));
+    OFB_CUDA_TRY(cudaStreamSynchronize(st));
+    return OFB_OK;
+}
+
+int ofb_bilateral_planar_device(ofb_ctx *c, const uint8_t *gray_d, size_t pitch, int w, int h, int ww, int wh, double sigmaS,
+                                double sigmaB, uint8_t *dst_d, size_t dst_pitch, void *stream)
+{
+    OFB_CHECK_CTX(c);
+    if (!gray_d || !dst_d) {
+        set_error("NULL image pointer");
+        return OFB_ERR_INVALID;
+    }
+    OFB_GUARD(c);
+    if (!c->bil_lut) OFB_CUDA_TRY(cudaMalloc(reinterpret_cast<void **>(&c->bil_lut), 256 * sizeof(double)));
+    return launch_bilateral(gray_d, gray_d, pitch, 1, w, h, ww, wh, sigmaS, sigmaB, c->bil_lut, dst_d, dst_pitch,
+                            static_cast<cudaStream_t>(stream), &c->launches);
+}
+
+} // extern "C"
+
+// One frame sequence: two device-resident planar pyramids that swap roles every frame (main.cu:270-272).
+struct ofb_stream {
+    ofb_ctx *ctx = nullptr;
+    ofb_params p{};
+    int bil_win = 0;
+    double sig_s = 0, sig_b = 0;
+    int frames = 0;
+    uint8_t *mem = nullptr; // all device buffers of the stream in one allocation
+    size_t pitch[OFB_MAX_LEVELS] = {}, off_pyr[2][OFB_MAX_LEVELS] = {}, off_bgr = 0, off_gray = 0, off_lut = 0;
+    size_t off_flow[OFB_MAX_LEVELS] = {}, off_cum[OFB_MAX_LEVELS] = {}, off_total = 0;
+    int cur = 0; // which pyramid receives the next frame
+};
+
+extern "C" {
+
+int ofb_stream_create(ofb_ctx *c, const ofb_params *p, int bil_win, double bil_sigma_s, double bil_sigma_b, ofb_stream **out)
+{
+    OFB_CHECK_CTX(c);
+    if (!out) {
+        set_error("out is NULL");
+        return OFB_ERR_INVALID;
+    }
+    *out = nullptr;
+    int rc = check_params(p);
+    if (rc) return rc;
+    if (p->n_pairs != 1) {
+        set_error("a frame sequence solves one pair per frame (n_pairs must be 1)");
+        return OFB_ERR_INVALID;
+    }
+    if (bil_win != 0 && (bil_win < 3 || bil_win > 9 || !(bil_win & 1))) {
+        set_error("bilateral window %d not supported (0 = off, or odd 3..9)", bil_win);
+        return OFB_ERR_UNSUPPORTED;
+    }
+    OFB_GUARD(c);
+    ofb_stream *s = new (std::nothrow) ofb_stream();
+    if (!s) {
+        set_error("out of host memory");
+        return OFB_ERR_NOMEM;
+    }
+    s->ctx = c;
+    s->p = *p;
+    s->bil_win = bil_win;
+    s->sig_s = bil_sigma_s;
+    s->sig_b = bil_sigma_b;
+    Carver cv;
+    s->off_bgr = cv.take((size_t)p->w * p->h * 3);
+    for (int k = 0; k < p->levels; k++) {
+        const int wk = p->w >> k, hk = p->h >> k;
+        s->pitch[k] = align_up((size_t)wk, 64);
+        s->off_pyr[0][k] = cv.take(s->pitch[k] * hk);
+        s->off_pyr[1][k] = cv.take(s->pitch[k] * hk);
+        s->off_flow[k] = cv.take((size_t)wk * hk * 8);
+        s->off_cum[k] = cv.take((size_t)wk * hk * 8);
+    }
+    s->off_gray = cv.take(s->pitch[0] * p->h);
+    s->off_total = cv.take((size_t)p->w * p->h * 8);
+    s->off_lut = cv.take(256 * sizeof(double));
+    cudaError_t e = cudaMalloc(reinterpret_cast<void **>(&s->mem), cv.off);
+    if (e != cudaSuccess) {
+        set_error("stream cudaMalloc(%zu) failed: %s", cv.off, cudaGetErrorString(e));
+        cudaGetLastError();
+        delete s;
+        return OFB_ERR_NOMEM;
+    }
+    OFB_CUDA_TRY(cudaMemsetAsync(s->mem, 0, cv.off, c->stream));
+    *out = s;
+    return OFB_OK;
+}
+
+int ofb_stream_destroy(ofb_stream *s)
+{
+    if (!s) {
+        set_error("stream is NULL");
+        return OFB_ERR_INVALID;
+    }
+    {
+        DeviceGuard g(s->ctx->device);
+        if (g.ok) {
+            cudaStreamSynchronize(s->ctx->stream);
+            if (s->mem) cudaFree(s->mem);
+        }
+    }
+    delete s;
+    return OFB_OK;
+}
+
+int ofb_stream_push_bgr_host(ofb_stream *s, const unsigned char *frame_bgr, float *const *flow_levels_h, float *total_flow_h,
+                             int *has_flow)
+{
+    if (!s || !frame_bgr) {
+        set_error("stream_push: NULL stream or frame");
+        return OFB_ERR_INVALID;
+    }
+    ofb_ctx *c = s->ctx;
+    OFB_GUARD(c);
+    const ofb_params &p = s->p;
+    cudaStream_t st = c->stream;
+    uint8_t *B = s->mem;
+    const int cur = s->cur, prv = cur ^ 1;
+    if (has_flow) *has_flow = 0;
+    // upload, grayscale (main.cu:232), bilateral pre-filter (main.cu:240) into level 0 of the current pyramid
+    OFB_CUDA_TRY(cudaMemcpyAsync(B + s->off_bgr, frame_bgr, (size_t)p.w * p.h * 3, cudaMemcpyHostToDevice, st));
+    uint8_t *lvl0 = B + s->off_pyr[cur][0];
+    int rc = launch_grayscale(B + s->off_bgr, p.w, p.h, nullptr, s->bil_win ? B + s->off_gray : lvl0, s->pitch[0], st,
+                              &c->launches);
+    if (rc) return rc;
+    if (s->bil_win) {
+        rc = launch_bilateral(B + s->off_gray, B + s->off_gray, s->pitch[0], 1, p.w, p.h, s->bil_win, s->bil_win, s->sig_s,
+                              s->sig_b, reinterpret_cast<double *>(B + s->off_lut), lvl0, s->pitch[0], st, &c->launches);
+        if (rc) return rc;
+    }
+    for (int k = 1; k < p.levels; k++) { // main.cu:250
+        rc = launch_pyr_down(B + s->off_pyr[cur][k - 1], s->pitch[k - 1], 0, p.w >> (k - 1), p.h >> (k - 1),
+                             B + s->off_pyr[cur][k], s->pitch[k], 0, 1, 1, st, &c->launches);
+        if (rc) return rc;
+    }
+    if (s->frames > 0) {
+        if (!flow_levels_h) {
+            set_error("stream_push: flow_levels_h is NULL");
+            return OFB_ERR_INVALID;
+        }
+        for (int k = p.levels - 1; k >= 0; k--) { // main.cu:256-262
+            LkLevelArgs a{};
+            a.prev = B + s->off_pyr[prv][k];
+            a.next = B + s->off_pyr[cur][k];
+            a.pitch = s->pitch[k];
+            a.image_stride = s->pitch[k] * (size_t)(p.h >> k);
+            a.w = p.w >> k;
+            a.h_local = a.h_global = p.h >> k;
+            a.out_y1 = p.h >> k;
+            a.n_pairs = 1;
+            a.win = p.win;
+            a.warp_mode = p.warp_mode;
+            a.flow_scale = p.flow_scale;
+            a.flow_out = reinterpret_cast<float *>(B + s->off_flow[k]);
+            a.sm_count = c->sm_count;
+            if (k < p.levels - 1) {
+                a.cum_in = reinterpret_cast<const float *>(k + 1 == p.levels - 1 ? B + s->off_flow[k + 1] : B + s->off_cum[k + 1]);
+                a.cum_w = p.w >> (k + 1);
+                a.cum_h_global = a.cum_h_local = p.h >> (k + 1);
+            }
+            if (k == 0) a.cum_out = total_flow_h ? reinterpret_cast<float *>(B + s->off_total) : nullptr;
+            else if (k <= p.levels - 2) a.cum_out = reinterpret_cast<float *>(B + s->off_cum[k]);
+            rc = launch_lk_level(a, st, &c->launches);
+            if (rc) return rc;
+            if (!flow_levels_h[k]) {
+                set_error("stream_push: flow_levels_h[%d] is NULL", k);
+                return OFB_ERR_INVALID;
+            }
+            OFB_CUDA_TRY(cudaMemcpyAsync(flow_levels_h[k], B + s->off_flow[k], (size_t)(p.w >> k) * (p.h >> k) * 8,
+                                         cudaMemcpyDeviceToHost, st));
+        }
+        if (total_flow_h)
+            OFB_CUDA_TRY(cudaMemcpyAsync(total_flow_h, B + s->off_total, (size_t)p.w * p.h * 8, cudaMemcpyDeviceToHost, st));
+        if (has_flow) *has_flow = 1;
+    }
+    OFB_CUDA_TRY(cudaStreamSynchronize(st));
+    s->cur = prv; // main.cu:270-272: the current pyramid becomes the previous one
+    s->frames++;
     return OFB_OK;
 }
 

@@ -68,6 +68,12 @@ int launch_inverse_f32(const float *sxx, const float *syy, const float *sxy, con
 int launch_compose_cum(const float *flow_k, const float *cum_coarser, int w, int h, int n_pairs, float *cum_out,
                        cudaStream_t stream, unsigned long long *launches);
 
+int launch_grayscale(const uint8_t *src_c3, int w, int h, uint8_t *dst_c3, uint8_t *dst_planar, size_t dst_pitch,
+                     cudaStream_t stream, unsigned long long *launches);
+int launch_bilateral(const uint8_t *src, const uint8_t *gray, size_t pitch, int channels, int w, int h, int ww, int wh,
+                     double sigmaS, double sigmaB, double *lut_dev, uint8_t *dst, size_t dst_pitch, cudaStream_t stream,
+                     unsigned long long *launches);
+
 // cuTensorMapEncodeTiled resolved through the runtime (no link-time libcuda dependency).
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                     const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,

@@ -191,3 +191,165 @@ int launch_compose_cum(const float *flow_k, const float *cum_coarser, int w, int
 }
 
 } // namespace ofb
+
+// =============================================================================================
+// Pre-processing of the reference's frame loop: grayscale and the bilateral
+// pre-filter that main.cu:232-240 applies to every new frame before the pyramid.
+// =============================================================================================
+namespace ofb {
+
+// g_grayscale_avg_2d, OptFlowGpu.cu:47-60: avg = (c0 + c1 + c2) / 3 (integer division), written to
+// all three channels (c3 -> c3, for the drop-in wrapper) or to a planar image (hot path).
+__global__ void __launch_bounds__(256)
+grayscale_kernel(const uint8_t *__restrict__ src, int w, int h, uint8_t *__restrict__ dst_c3, uint8_t *__restrict__ dst_planar,
+                 size_t dst_pitch)
+{
+    const int x = blockIdx.x * 256 + threadIdx.x, y = blockIdx.y;
+    if (x >= w) return;
+    const size_t pos = ((size_t)y * w + x) * 3;
+    const int avg = ((int)__ldg(src + pos) + (int)__ldg(src + pos + 1) + (int)__ldg(src + pos + 2)) / 3;
+    if (dst_c3) dst_c3[pos] = dst_c3[pos + 1] = dst_c3[pos + 2] = (uint8_t)avg;
+    if (dst_planar) dst_planar[(size_t)y * dst_pitch + x] = (uint8_t)avg;
+}
+
+int launch_grayscale(const uint8_t *src_c3, int w, int h, uint8_t *dst_c3, uint8_t *dst_planar, size_t dst_pitch,
+                     cudaStream_t stream, unsigned long long *launches)
+{
+    if (w < 1 || h < 1 || h > 65535) {
+        set_error("grayscale: bad geometry (w %d h %d)", w, h);
+        return OFB_ERR_INVALID;
+    }
+    dim3 grid((unsigned)((w + 255) / 256), (unsigned)h);
+    grayscale_kernel<<<grid, 256, 0, stream>>>(src_c3, w, h, dst_c3, dst_planar, dst_pitch);
+    OFB_CUDA_TRY(cudaGetLastError());
+    if (launches) ++*launches;
+    return OFB_OK;
+}
+
+// Range weights of g_bilinear_filter (OptFlowGpu.cu:1984-2048; a bilateral filter despite its name):
+//   n_b(k) = 1/(2*pi*sigmaB^2) * pow(e, -0.5*k^2/sigmaB^2),  k = gray(tap) - gray(centre) in -255..255.
+// The reference evaluates this per tap; it depends on |k| only, so a 256-entry table built with the
+// same double-precision operation order (read from the reference TU's SASS: (k*k*-0.5)/sigmaB2, pow,
+// times the hoisted 1/(2*pi*sigmaB2)) gives bit-identical weights at 1/81 of the pow calls.
+__global__ void bilateral_lut_kernel(double sigmaB, double *__restrict__ lut)
+{
+    const int d = threadIdx.x; // 0..255
+    const double sigmaB2 = sigmaB * sigmaB;
+    const double pref = 1.0 / (2.0 * M_PI * sigmaB2);
+    const double k = (double)d;
+    const double k2 = k * k;
+    lut[d] = pref * pow(M_E, -0.5 * (k2) / sigmaB2);
+}
+
+struct SpatialMask {
+    double m[100]; // up to 10x10, like the reference's gaus_kernel_10x10_gpu (OptFlowGpu.cu:1982)
+};
+
+// One output per thread; gray tile with halo and the range table in shared memory.
+//   wsb = fma(n_b, n_s, wsb);  tmp_c = fma(n_s, n_b*src_c, tmp_c)   in row-major tap order,
+//   out-of-image taps skipped; dest_c = (unsigned char)(tmp_c / wsb)  -- the reference's order.
+// CH = 1: planar, src == gray (the main.cu use).  CH = 3: interleaved src and gray (drop-in wrapper).
+constexpr int BIL_BX = 32, BIL_BY = 8;
+template <int CH>
+__global__ void __launch_bounds__(BIL_BX *BIL_BY)
+bilateral_kernel(const uint8_t *__restrict__ src, const uint8_t *__restrict__ gray, size_t pitch, int w, int h, int ww,
+                 int wh, const double *__restrict__ lut_g, SpatialMask sm, uint8_t *__restrict__ dst, size_t dst_pitch)
+{
+    extern __shared__ __align__(16) uint8_t smem_b[];
+    double *lut = reinterpret_cast<double *>(smem_b);
+    uint8_t *tile = smem_b + 256 * sizeof(double);
+    const int tw = BIL_BX + ww - 1, th = BIL_BY + wh - 1;
+    const int hww = ww >> 1, hwh = wh >> 1;
+    const int bx0 = blockIdx.x * BIL_BX - hww, by0 = blockIdx.y * BIL_BY - hwh;
+    const int tid = threadIdx.y * BIL_BX + threadIdx.x;
+    for (int t = tid; t < 256; t += BIL_BX * BIL_BY) lut[t] = lut_g[t];
+    for (int t = tid; t < tw * th; t += BIL_BX * BIL_BY) {
+        const int ty = t / tw, tx = t - ty * tw;
+        const int gx = bx0 + tx, gy = by0 + ty;
+        tile[t] = (gx >= 0 && gx < w && gy >= 0 && gy < h) ? __ldg(gray + (size_t)gy * pitch + (size_t)gx * CH) : 0;
+    }
+    __syncthreads();
+    const int x = blockIdx.x * BIL_BX + threadIdx.x, y = blockIdx.y * BIL_BY + threadIdx.y;
+    if (x >= w || y >= h) return;
+    const int f_ij = tile[(threadIdx.y + hwh) * tw + threadIdx.x + hww];
+    double wsb = 0.0, tmp[CH];
+#pragma unroll
+    for (int c = 0; c < CH; c++) tmp[c] = 0.0;
+    for (int m = 0; m < wh; m++) {
+        const int cy = y - hwh + m;
+        if (cy < 0 || cy >= h) continue;
+        for (int n = 0; n < ww; n++) {
+            const int cx = x - hww + n;
+            if (cx < 0 || cx >= w) continue;
+            const int f_mn = tile[(threadIdx.y + m) * tw + threadIdx.x + n];
+            const int k = f_mn - f_ij;
+            const double n_b = lut[k < 0 ? -k : k];
+            const double n_s = sm.m[m * ww + n];
+            wsb = __fma_rn(n_b, n_s, wsb);
+            if (CH == 1) {
+                tmp[0] = __fma_rn(n_s, __dmul_rn(n_b, (double)f_mn), tmp[0]);
+            } else {
+                const uint8_t *sp = src + (size_t)cy * pitch + (size_t)cx * CH;
+#pragma unroll
+                for (int c = 0; c < CH; c++) tmp[c] = __fma_rn(n_s, __dmul_rn(n_b, (double)__ldg(sp + c)), tmp[c]);
+            }
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < CH; c++) dst[(size_t)y * dst_pitch + (size_t)x * CH + c] = (uint8_t)(unsigned int)(tmp[c] / wsb);
+}
+
+// utils::generate_gaussian_kernel, OptFlowUtils.cpp:68-114 (host, double, libm pow): the normalised
+// spatial Gaussian the reference uploads into its __constant__ table.  Same arithmetic, same order.
+static int make_spatial_mask(double sigmaS, int ksize, SpatialMask *out)
+{
+    if (ksize < 1 || ksize > 10 || (ksize & 1) == 0) {
+        set_error("bilateral: spatial window %d not supported (odd, at most 9; the reference's table holds 10x10)", ksize);
+        return OFB_ERR_UNSUPPORTED;
+    }
+    const int hk = ksize >> 1;
+    double *g = out->m;
+    for (int i = 0; i < hk + 1; i++)
+        for (int j = 0; j < hk + 1; j++) {
+            const double sigmaS2 = sigmaS * sigmaS;
+            const double m = i, n = j;
+            const double n2 = n * n, m2 = m * m;
+            const double value = 1.0 / (2.0 * M_PI * sigmaS2) * pow(M_E, -0.5 * (n2 + m2) / sigmaS2);
+            g[(hk + i) * ksize + hk + j] = value;
+            g[(hk - i) * ksize + hk - j] = value;
+            g[(hk + i) * ksize + hk - j] = value;
+            g[(hk - i) * ksize + hk + j] = value;
+        }
+    double sum = 0;
+    for (int i = 0; i < ksize * ksize; i++) sum += g[i];
+    for (int i = 0; i < ksize * ksize; i++) g[i] /= sum;
+    return OFB_OK;
+}
+
+int launch_bilateral(const uint8_t *src, const uint8_t *gray, size_t pitch, int channels, int w, int h, int ww, int wh,
+                     double sigmaS, double sigmaB, double *lut_dev, uint8_t *dst, size_t dst_pitch, cudaStream_t stream,
+                     unsigned long long *launches)
+{
+    if (w < 1 || h < 1 || ww != wh || (channels != 1 && channels != 3)) {
+        set_error("bilateral: bad arguments (w %d h %d window %dx%d channels %d; the window must be square)", w, h, ww, wh,
+                  channels);
+        return OFB_ERR_INVALID;
+    }
+    SpatialMask sm;
+    int rc = make_spatial_mask(sigmaS, ww, &sm);
+    if (rc) return rc;
+    bilateral_lut_kernel<<<1, 256, 0, stream>>>(sigmaB, lut_dev);
+    OFB_CUDA_TRY(cudaGetLastError());
+    if (launches) ++*launches;
+    const size_t smem = 256 * sizeof(double) + (size_t)(BIL_BX + ww - 1) * (BIL_BY + wh - 1);
+    dim3 block(BIL_BX, BIL_BY), grid((unsigned)((w + BIL_BX - 1) / BIL_BX), (unsigned)((h + BIL_BY - 1) / BIL_BY));
+    if (channels == 1)
+        bilateral_kernel<1><<<grid, block, smem, stream>>>(src, gray, pitch, w, h, ww, wh, lut_dev, sm, dst, dst_pitch);
+    else
+        bilateral_kernel<3><<<grid, block, smem, stream>>>(src, gray, pitch, w, h, ww, wh, lut_dev, sm, dst, dst_pitch);
+    OFB_CUDA_TRY(cudaGetLastError());
+    if (launches) ++*launches;
+    return OFB_OK;
+}
+
+} // namespace ofb

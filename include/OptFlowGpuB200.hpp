@@ -112,4 +112,21 @@ inline void inverse_matrix_float(float *sumIx2, float *sumIy2, float *sumIxIy, f
            ofb_inverse_matrix_f32_host(c, sumIx2, sumIy2, sumIxIy, sumIxIt, sumIyIt, optFlowPyramid, level, w, h));
 }
 
+// OptFlowGpu.cuh:5 (height before width, like the reference).
+inline void grayscale_avg(const unsigned char *src_h, unsigned char *dest_h, int h, int w)
+{
+    ofb_ctx *c = default_context();
+    if (!c) return;
+    report("grayscale_avg", ofb_grayscale_avg_host_u8c3(c, src_h, dest_h, h, w));
+}
+
+// OptFlowGpu.cuh:35 (a bilateral filter despite its name).
+inline void bilinear_filter(unsigned char *src, unsigned char *gray, unsigned char *dest, int w, int h, int ww, int wh,
+                            double sigmaS, double sigmaB)
+{
+    ofb_ctx *c = default_context();
+    if (!c) return;
+    report("bilinear_filter", ofb_bilinear_filter_host_u8c3(c, src, gray, dest, w, h, ww, wh, sigmaS, sigmaB));
+}
+
 } // namespace gpu

@@ -161,6 +161,38 @@ int ofb_inverse_matrix_f32_host(ofb_ctx *ctx, const float *sumIx2, const float *
 int ofb_flow_pairs_host(ofb_ctx *ctx, const ofb_params *p, const unsigned char *prev_h, const unsigned char *next_h,
                         int channels, float *const *flow_levels_h);
 
+/* ------------------------------------------------------------------------------------------
+ * Pre-processing and the frame loop of main.cu
+ * ---------------------------------------------------------------------------------------- */
+
+/* gpu::grayscale_avg(src_h, dest_h, h, w), OptFlowGpu.cuh:5 / OptFlowGpu.cu:47-95: (c0+c1+c2)/3 into all
+ * three channels.  NOTE the reference's argument order: height before width. */
+int ofb_grayscale_avg_host_u8c3(ofb_ctx *ctx, const unsigned char *src_h, unsigned char *dest_h, int h, int w);
+
+/* gpu::bilinear_filter(src, gray, dest, w, h, ww, wh, sigmaS, sigmaB), OptFlowGpu.cuh:35 /
+ * OptFlowGpu.cu:1984-2083: despite the name a bilateral filter (spatial Gaussian sigmaS x range Gaussian
+ * sigmaB on gray channel 0), double precision, square odd window up to 9x9, 3-channel host images. */
+int ofb_bilinear_filter_host_u8c3(ofb_ctx *ctx, const unsigned char *src, const unsigned char *gray, unsigned char *dest,
+                                  int w, int h, int ww, int wh, double sigmaS, double sigmaB);
+
+/* The same filter on a device-resident planar gray image (src == gray, the way main.cu:240 uses it). */
+int ofb_bilateral_planar_device(ofb_ctx *ctx, const uint8_t *gray_d, size_t pitch, int w, int h, int ww, int wh,
+                                double sigmaS, double sigmaB, uint8_t *dst_d, size_t dst_pitch, void *stream);
+
+/* Frame sequence in the role of main.cu:222-275.  Each pushed BGR frame (3-channel interleaved host
+ * buffer) is uploaded once, converted to gray (main.cu:232), optionally bilateral-filtered (main.cu:240;
+ * bil_win = 0 disables it), turned into a pyramid (main.cu:250) and solved against the PREVIOUS frame's
+ * pyramid, which stays on the device (the swap of main.cu:270-272) -- half the pyramid work and no
+ * re-upload.  The first push only primes the pyramid (*has_flow = 0).
+ *   flow_levels_h[k]: residual flow of level k, (h>>k)*(w>>k)*2 floats; total_flow_h: optional level-0
+ *   composition (main.cu:136-147). */
+typedef struct ofb_stream ofb_stream;
+int ofb_stream_create(ofb_ctx *ctx, const ofb_params *p, int bil_win, double bil_sigma_s, double bil_sigma_b,
+                      ofb_stream **out);
+int ofb_stream_push_bgr_host(ofb_stream *s, const unsigned char *frame_bgr, float *const *flow_levels_h,
+                             float *total_flow_h, int *has_flow);
+int ofb_stream_destroy(ofb_stream *s);
+
 /* Pinned host memory helpers for callers without a CUDA runtime of their own. */
 int ofb_host_alloc(void **ptr, size_t bytes);
 int ofb_host_free(void *ptr);

@@ -17,6 +17,8 @@
  * and its LK stages read channel 0 only (OptFlowGpu.cu:1081), its pyramid treats the channels
  * independently (OptFlowGpu.cu:1224-1226), so planar is the same arithmetic on 1/3 of the bytes.
  */
+#define _USE_MATH_DEFINES
+#define _GNU_SOURCE
 #include <math.h>
 #include <stdint.h>
 #include <stdlib.h>
@@ -414,6 +416,75 @@ int orc_flow_pair(const uint8_t *prev0, const uint8_t *next0, int W0, int H0, in
         free(pn[k]);
     }
     return 0;
+}
+
+/* ---------------------------------------------------------------------------------------------
+ * 8f rows 1-2: the pre-processing of main.cu:232-240.
+ * Grayscale, OptFlowGpu.cu:47-60 (g_grayscale_avg_2d): (c0 + c1 + c2) / 3, integer division, written to
+ * all three channels.  3-channel interleaved in and out.
+ * ------------------------------------------------------------------------------------------- */
+void orc_grayscale_c3(const uint8_t *src, int w, int h, uint8_t *dst)
+{
+    for (size_t i = 0; i < (size_t)w * h; i++) {
+        const int avg = (src[3 * i] + src[3 * i + 1] + src[3 * i + 2]) / 3;
+        dst[3 * i] = dst[3 * i + 1] = dst[3 * i + 2] = (uint8_t)avg;
+    }
+}
+
+/* utils::generate_gaussian_kernel, OptFlowUtils.cpp:68-114: value(i,j) = 1/(2 pi s^2) * e^(-(i^2+j^2)/(2 s^2))
+ * mirrored into the four quadrants, then divided by the sum of the whole mask. */
+void orc_gaussian_kernel(double sigmaS, int ksize, double *g)
+{
+    const int hk = ksize >> 1;
+    for (int i = 0; i < hk + 1; i++)
+        for (int j = 0; j < hk + 1; j++) {
+            const double s2 = sigmaS * sigmaS, m = i, n = j;
+            const double value = 1.0 / (2.0 * M_PI * s2) * pow(M_E, -0.5 * (n * n + m * m) / s2);
+            g[(hk + i) * ksize + hk + j] = g[(hk - i) * ksize + hk - j] = value;
+            g[(hk + i) * ksize + hk - j] = g[(hk - i) * ksize + hk + j] = value;
+        }
+    double sum = 0;
+    for (int i = 0; i < ksize * ksize; i++) sum += g[i];
+    for (int i = 0; i < ksize * ksize; i++) g[i] /= sum;
+}
+
+/* Bilateral pre-filter, OptFlowGpu.cu:1984-2048 (g_bilinear_filter; same arithmetic in
+ * OptFlowCPU.cpp:401-465): for every pixel, over the ww x wh window (out-of-image taps skipped, row-major)
+ *   n_b = 1/(2 pi sB^2) * e^(-0.5 (gray(tap) - gray(centre))^2 / sB^2),  n_s = spatial mask
+ *   wsb += n_b*n_s;  tmp_c += src_c(tap) * n_b * n_s;   dest_c = (unsigned char)(tmp_c / wsb)
+ * all in double, range weights from channel 0 of `gray`.  The fma contraction below is the one nvcc emits
+ * for the GPU kernel (wsb = fma(n_b, n_s, wsb); tmp = fma(n_s, n_b*src, tmp)).  libm's pow and CUDA's pow
+ * may differ in the last bit, so against the GPU this restatement is exact up to rare 1-level flips where
+ * tmp/wsb lands within an ulp of an integer; the tests state that tolerance. */
+void orc_bilateral_c3(const uint8_t *src, const uint8_t *gray, int w, int h, int ww, int wh, double sigmaS, double sigmaB,
+                      uint8_t *dst)
+{
+    double *mask = (double *)malloc((size_t)ww * wh * sizeof(double));
+    orc_gaussian_kernel(sigmaS, ww, mask);
+    const int hww = ww >> 1, hwh = wh >> 1;
+    const double sB2 = sigmaB * sigmaB;
+    const double pref = 1.0 / (2.0 * M_PI * sB2);
+    for (int y = 0; y < h; y++)
+        for (int x = 0; x < w; x++) {
+            const double f_ij = gray[((size_t)y * w + x) * 3];
+            double wsb = 0, tmp[3] = {0, 0, 0};
+            for (int m = 0; m < wh; m++) {
+                const int cy = y - hwh + m;
+                if (cy < 0 || cy >= h) continue;
+                for (int n = 0; n < ww; n++) {
+                    const int cx = x - hww + n;
+                    if (cx < 0 || cx >= w) continue;
+                    const size_t cp = ((size_t)cy * w + cx) * 3;
+                    const double k = (double)gray[cp] - f_ij;
+                    const double n_b = pref * pow(M_E, -0.5 * (k * k) / sB2);
+                    const double n_s = mask[m * ww + n];
+                    wsb = fma(n_b, n_s, wsb);
+                    for (int c = 0; c < 3; c++) tmp[c] = fma(n_s, n_b * (double)src[cp + c], tmp[c]);
+                }
+            }
+            for (int c = 0; c < 3; c++) dst[((size_t)y * w + x) * 3 + c] = (uint8_t)(unsigned int)(tmp[c] / wsb);
+        }
+    free(mask);
 }
 
 /* ---------------------------------------------------------------------------------------------

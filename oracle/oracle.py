@@ -169,6 +169,35 @@ def flow_pair(prev0: np.ndarray, next0: np.ndarray, levels: int, win: int, warp_
     return (flows, cums) if want_cum else flows
 
 
+def grayscale_c3(src_c3: np.ndarray) -> np.ndarray:
+    h, w, _ = src_c3.shape
+    src_c3 = np.ascontiguousarray(src_c3, np.uint8)
+    dst = np.empty_like(src_c3)
+    lib().orc_grayscale_c3(_p(src_c3, _u8p), w, h, _p(dst, _u8p))
+    return dst
+
+
+def gaussian_kernel(sigma_s: float, ksize: int) -> np.ndarray:
+    g = np.empty((ksize, ksize), np.float64)
+    lib().orc_gaussian_kernel(C.c_double(sigma_s), ksize, g.ctypes.data_as(C.POINTER(C.c_double)))
+    return g
+
+
+def bilateral_c3(src_c3: np.ndarray, gray_c3: np.ndarray, ww: int, wh: int, sigma_s: float, sigma_b: float) -> np.ndarray:
+    h, w, _ = src_c3.shape
+    src_c3 = np.ascontiguousarray(src_c3, np.uint8)
+    gray_c3 = np.ascontiguousarray(gray_c3, np.uint8)
+    dst = np.empty_like(src_c3)
+    lib().orc_bilateral_c3(_p(src_c3, _u8p), _p(gray_c3, _u8p), w, h, ww, wh, C.c_double(sigma_s), C.c_double(sigma_b),
+                           _p(dst, _u8p))
+    return dst
+
+
+def make_bgr_frame(w: int, h: int, dx: float = 0.0, dy: float = 0.0, cell: int = 8, seed: int = 1) -> np.ndarray:
+    """Three different value-noise channels (a colour frame for the grayscale / frame-loop tests)."""
+    return np.ascontiguousarray(np.stack([make_frame(w, h, dx, dy, cell, seed + 17 * c) for c in range(3)], axis=2))
+
+
 # ------------------------------------------------------------------ helpers shared by tests
 def to_c3(img: np.ndarray) -> np.ndarray:
     """Planar gray -> the reference's 3-equal-channel interleaved layout (OptFlowGpu.cu:58-59)."""
@@ -207,6 +236,42 @@ def ref_cpu_flow_pair_c3(prev_c3: np.ndarray, next_c3: np.ndarray, levels: int) 
     ref().ref_cpu_flow_pair(_p(np.ascontiguousarray(prev_c3), _u8p), _p(np.ascontiguousarray(next_c3), _u8p), w, h,
                             levels, _ptr_array(flows, _f32p))
     return flows
+
+
+def ref_cpu_grayscale(src_c3: np.ndarray) -> np.ndarray:
+    h, w, _ = src_c3.shape
+    dst = np.empty_like(src_c3)
+    ref().ref_cpu_grayscale_avg(_p(np.ascontiguousarray(src_c3), _u8p), _p(dst, _u8p), w, h)
+    return dst
+
+
+def ref_gaussian_kernel(sigma_s: float, ksize: int) -> np.ndarray:
+    g = np.empty((ksize, ksize), np.float64)
+    ref().ref_utils_generate_gaussian_kernel(C.c_double(sigma_s), ksize, g.ctypes.data_as(C.POINTER(C.c_double)))
+    return g
+
+
+def ref_cpu_bilateral(src_c3, gray_c3, ww, wh, sigma_s, sigma_b) -> np.ndarray:
+    h, w, _ = src_c3.shape
+    dst = np.empty_like(src_c3)
+    ref().ref_cpu_bilinear_filter_3ch(_p(np.ascontiguousarray(src_c3).copy(), _u8p), _p(np.ascontiguousarray(gray_c3).copy(), _u8p),
+                                      _p(dst, _u8p), w, h, ww, wh, C.c_double(sigma_s), C.c_double(sigma_b))
+    return dst
+
+
+def ref_gpu_grayscale(src_c3: np.ndarray) -> np.ndarray:
+    h, w, _ = src_c3.shape
+    dst = np.empty_like(src_c3)
+    ref().ref_gpu_grayscale_avg(_p(np.ascontiguousarray(src_c3), _u8p), _p(dst, _u8p), h, w)
+    return dst
+
+
+def ref_gpu_bilateral(src_c3, gray_c3, ww, wh, sigma_s, sigma_b) -> np.ndarray:
+    h, w, _ = src_c3.shape
+    dst = np.zeros_like(src_c3)
+    ref().ref_gpu_bilinear_filter(_p(np.ascontiguousarray(src_c3).copy(), _u8p), _p(np.ascontiguousarray(gray_c3).copy(), _u8p),
+                                  _p(dst, _u8p), w, h, ww, wh, C.c_double(sigma_s), C.c_double(sigma_b))
+    return dst
 
 
 def ref_gpu_conv(src_c3: np.ndarray, mask: np.ndarray) -> np.ndarray:

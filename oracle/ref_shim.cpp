@@ -68,6 +68,26 @@ void ref_cpu_flow_pair(const unsigned char *prev0, const unsigned char *next0, i
     free(pn);
 }
 
+void ref_cpu_grayscale_avg(const unsigned char *src, unsigned char *dest, int w, int h)
+{
+    cpu::grayscale_avg_cpu(src, dest, w, h);
+}
+void ref_cpu_bilinear_filter_3ch(unsigned char *src, unsigned char *gray, unsigned char *dest, int w, int h, int ww, int wh,
+                                 double sigmaS, double sigmaB)
+{
+    cpu::bilinear_filter_3ch(src, gray, dest, w, h, ww, wh, sigmaS, sigmaB);
+}
+void ref_utils_generate_gaussian_kernel(double sigmaS, int kernel_size, double *dest)
+{
+    utils::generate_gaussian_kernel(sigmaS, kernel_size, dest);
+}
+void ref_gpu_grayscale_avg(const unsigned char *src, unsigned char *dest, int h, int w) { gpu::grayscale_avg(src, dest, h, w); }
+void ref_gpu_bilinear_filter(unsigned char *src, unsigned char *gray, unsigned char *dest, int w, int h, int ww, int wh,
+                             double sigmaS, double sigmaB)
+{
+    gpu::bilinear_filter(src, gray, dest, w, h, ww, wh, sigmaS, sigmaB);
+}
+
 // ---- GPU-side functions of the reference (need a GPU; launch-valid only when w,h are multiples
 // of 32 and (w/32)*(h/32) <= 1024) ----
 void ref_gpu_gauss_pyramid(unsigned char **pyramid, int w, int h, int levels)
