@@ -7,53 +7,67 @@
 
 namespace ofb {
 
-// Planar u8, four outputs per thread: 3 rows x (1 + 8) source bytes, one 32-bit store.
+// Planar u8.  One thread = 8 output columns x 2 output rows: five source rows of 16 bytes (one
+// 128-bit load each; the byte left of them comes from the neighbouring lane by shuffle), horizontal
+// [1 2 1] on packed 16-bit pairs (values stay below 2^12), vertical [1 2 1] shared between the two
+// output rows, one 64-bit store per row.  Row strips: dst local row y is global row dst_y0 + y, src
+// local row 0 is global row src_y_off.
+__device__ __forceinline__ void pyr_hrow(const uint4 q, uint32_t left, uint32_t h[4])
+{
+    // bytes b0..b15; h[k] (k = 0..7, packed two per word) = b[2k-1] + 2*b[2k] + b[2k+1], b[-1] = left
+    const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+    uint32_t prev_odd = left << 16; // odd byte of the previous pair in the high half
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const uint32_t ev = __byte_perm(w[i], 0, 0x4240); // b0 | b2 << 16
+        const uint32_t od = __byte_perm(w[i], 0, 0x4341); // b1 | b3 << 16
+        const uint32_t odl = __funnelshift_l(prev_odd, od, 16); // (previous odd byte) | b1 << 16
+        h[i] = odl + 2 * ev + od;
+        prev_odd = od;
+    }
+}
+
 __global__ void __launch_bounds__(256)
 pyr_down_planar_kernel(const uint8_t *__restrict__ src, size_t src_pitch, size_t src_stride, int dw, int dh,
-                       uint8_t *__restrict__ dst, size_t dst_pitch, size_t dst_stride, int src_y_off, int dst_y0)
+                       uint8_t *__restrict__ dst, size_t dst_pitch, size_t dst_stride, int src_y_off, int dst_y0,
+                       int src_rows)
 {
-    // Row strips: dst local row y is global row dst_y0 + y; src local row 0 is global row src_y_off.
-    const int x0 = 4 * (blockIdx.x * 32 + threadIdx.x);
-    const int y = blockIdx.y * 8 + threadIdx.y;
-    if (x0 >= dw || y >= dh) return;
+    const int tx = blockIdx.x * 32 + threadIdx.x;
+    const int x0 = 8 * tx;
+    const int y = 2 * (blockIdx.y * 8 + threadIdx.y);
+    // whole warps stay alive for the shuffle; lanes past the row only skip their loads and stores
+    const bool live = x0 < dw && y < dh;
     const uint8_t *s = src + (size_t)blockIdx.z * src_stride;
-    uint8_t *d = dst + (size_t)blockIdx.z * dst_stride + (size_t)y * dst_pitch + x0;
-    const bool wide = (size_t)(2 * x0 + 8) <= src_pitch; // the 8-byte load stays inside this row's pitch
-    int acc[4] = {0, 0, 0, 0};
+    const bool two = y + 1 < dh;
+    uint32_t h[5][4];
 #pragma unroll
-    for (int r = 0; r < 3; r++) {
+    for (int r = 0; r < 5; r++) {
         const int sg = 2 * (dst_y0 + y) - 1 + r; // global source row; above the image: skipped
-        if (sg < 0) continue;
         const int sy = sg - src_y_off;
-        const uint8_t *row = s + (size_t)sy * src_pitch + 2 * x0;
-        int v[9];
-        v[0] = (x0 > 0) ? (int)__ldg(row - 1) : 0;
-        if (wide) {
-            const uint2 q = __ldg(reinterpret_cast<const uint2 *>(row));
-            v[1] = q.x & 255;
-            v[2] = (q.x >> 8) & 255;
-            v[3] = (q.x >> 16) & 255;
-            v[4] = q.x >> 24;
-            v[5] = q.y & 255;
-            v[6] = (q.y >> 8) & 255;
-            v[7] = (q.y >> 16) & 255;
-            v[8] = q.y >> 24;
+        const bool ok = live && sg >= 0 && sy < src_rows && (r < 3 || two);
+        uint4 q = make_uint4(0, 0, 0, 0);
+        if (ok) q = __ldg(reinterpret_cast<const uint4 *>(s + (size_t)sy * src_pitch + 2 * x0));
+        uint32_t left = __shfl_up_sync(0xffffffffu, q.w >> 24, 1);
+        if (threadIdx.x == 0) left = (ok && tx > 0) ? (uint32_t)__ldg(s + (size_t)sy * src_pitch + 2 * x0 - 1) : 0u;
+        pyr_hrow(q, left, h[r]);
+    }
+    if (!live) return;
+#pragma unroll
+    for (int o = 0; o < 2; o++) {
+        if (o == 1 && !two) break;
+        uint32_t v[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) v[i] = ((h[2 * o][i] + 2 * h[2 * o + 1][i] + h[2 * o + 2][i]) >> 4) & 0x00ff00ffu;
+        // v[i] holds outputs 2i (low half) and 2i+1 (high half), each already < 256
+        const uint32_t lo = __byte_perm(v[0], v[1], 0x6420), hi = __byte_perm(v[2], v[3], 0x6420);
+        uint8_t *d = dst + (size_t)blockIdx.z * dst_stride + (size_t)(y + o) * dst_pitch + x0;
+        if (x0 + 7 < dw && (reinterpret_cast<uintptr_t>(d) & 7) == 0) {
+            *reinterpret_cast<uint2 *>(d) = make_uint2(lo, hi);
         } else {
 #pragma unroll
-            for (int k = 0; k < 8; k++) v[1 + k] = ((size_t)(2 * x0 + k) < src_pitch) ? (int)__ldg(row + k) : 0;
+            for (int k = 0; k < 8; k++)
+                if (x0 + k < dw) d[k] = (uint8_t)(((k < 4 ? lo : hi) >> (8 * (k & 3))) & 255u);
         }
-        const int wr = (r == 1) ? 2 : 1;
-#pragma unroll
-        for (int k = 0; k < 4; k++) acc[k] += wr * (v[2 * k] + 2 * v[2 * k + 1] + v[2 * k + 2]);
-    }
-    if (x0 + 3 < dw) {
-        const uint32_t o = (uint32_t)(acc[0] >> 4) | ((uint32_t)(acc[1] >> 4) << 8) | ((uint32_t)(acc[2] >> 4) << 16) |
-                           ((uint32_t)(acc[3] >> 4) << 24);
-        *reinterpret_cast<uint32_t *>(d) = o;
-    } else {
-#pragma unroll
-        for (int k = 0; k < 4; k++)
-            if (x0 + k < dw) d[k] = (uint8_t)(acc[k] >> 4);
     }
 }
 
@@ -97,9 +111,14 @@ int launch_pyr_down_strip(const uint8_t *src, size_t src_pitch, int sw, int src_
         set_error("pyr_down_strip: planar images need 8-byte aligned source rows and 4-byte aligned destination rows");
         return OFB_ERR_INVALID;
     }
+    if ((src_pitch & 15) || (reinterpret_cast<uintptr_t>(src) & 15)) {
+        set_error("pyr_down_strip: source rows must be 16-byte aligned");
+        return OFB_ERR_INVALID;
+    }
     dim3 block(32, 8);
-    dim3 grid((unsigned)((dw + 127) / 128), (unsigned)((dh + 7) / 8), 1);
-    pyr_down_planar_kernel<<<grid, block, 0, stream>>>(src, src_pitch, 0, dw, dh, dst, dst_pitch, 0, src_y_off, dst_y0);
+    dim3 grid((unsigned)((dw + 255) / 256), (unsigned)((dh + 15) / 16), 1);
+    pyr_down_planar_kernel<<<grid, block, 0, stream>>>(src, src_pitch, 0, dw, dh, dst, dst_pitch, 0, src_y_off, dst_y0,
+                                                       src_rows);
     OFB_CUDA_TRY(cudaGetLastError());
     if (launches) ++*launches;
     return OFB_OK;
@@ -115,9 +134,8 @@ int launch_pyr_down(const uint8_t *src, size_t src_pitch, size_t src_stride, int
         return OFB_ERR_INVALID;
     }
     if (channels == 1) {
-        if ((src_pitch & 7) || (dst_pitch & 3) || (reinterpret_cast<uintptr_t>(src) & 7) ||
-            (reinterpret_cast<uintptr_t>(dst) & 3) || (src_stride & 7) || (dst_stride & 3)) {
-            set_error("pyr_down: planar images need 8-byte aligned source rows and 4-byte aligned destination rows");
+        if ((src_pitch & 15) || (reinterpret_cast<uintptr_t>(src) & 15) || (src_stride & 15)) {
+            set_error("pyr_down: planar source images need 16-byte aligned rows (pitch, base and image stride)");
             return OFB_ERR_INVALID;
         }
         if (n_images > 65535) {
@@ -125,8 +143,9 @@ int launch_pyr_down(const uint8_t *src, size_t src_pitch, size_t src_stride, int
             return OFB_ERR_INVALID;
         }
         dim3 block(32, 8);
-        dim3 grid((unsigned)((dw + 127) / 128), (unsigned)((dh + 7) / 8), (unsigned)n_images);
-        pyr_down_planar_kernel<<<grid, block, 0, stream>>>(src, src_pitch, src_stride, dw, dh, dst, dst_pitch, dst_stride, 0, 0);
+        dim3 grid((unsigned)((dw + 255) / 256), (unsigned)((dh + 15) / 16), (unsigned)n_images);
+        pyr_down_planar_kernel<<<grid, block, 0, stream>>>(src, src_pitch, src_stride, dw, dh, dst, dst_pitch, dst_stride, 0, 0,
+                                                           sh);
         OFB_CUDA_TRY(cudaGetLastError());
         if (launches) ++*launches;
     } else {
