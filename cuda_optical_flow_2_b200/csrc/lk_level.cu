@@ -1,5 +1,6 @@
-// lk_level.cu -- host-side launcher of the fused per-level LK kernel: tensor maps, grid sizing,
-// (window, warp mode) dispatch.
+// lk_level.cu -- host-side entry of the fused per-level LK kernel: tensor maps, argument checks and
+// the dispatch on the window size.  The kernels themselves are instantiated one window per
+// translation unit (lk_win.cu, compiled once per -DLK_WIN=n) so that the build runs in parallel.
 #include "lk_level.cuh"
 
 #include <mutex>
@@ -21,7 +22,7 @@ PFN_encodeTiled get_encode_tiled()
 }
 
 // u8 image batch as a 3-D tensor (x, y, image); box = LK_TILE_W x rows x 1; OOB reads give 0.
-static int make_image_map(CUtensorMap *tm, const uint8_t *base, int w, int h, int n, size_t pitch, size_t stride,
+int lk_make_image_map(CUtensorMap *tm, const uint8_t *base, int w, int h, int n, size_t pitch, size_t stride,
                           int box_rows)
 {
     PFN_encodeTiled enc = get_encode_tiled();
@@ -49,86 +50,7 @@ static int make_image_map(CUtensorMap *tm, const uint8_t *base, int w, int h, in
     return OFB_OK;
 }
 
-template <int WIN, int MODE>
-static int launch_one(const LkLevelArgs &a, cudaStream_t stream, unsigned long long *launches)
-{
-    using C = LkCfg<WIN>;
-    static bool attr_set[64] = {};
-    int dev = 0;
-    OFB_CUDA_TRY(cudaGetDevice(&dev));
-    if (dev < 64 && !attr_set[dev]) {
-        OFB_CUDA_TRY(cudaFuncSetAttribute(lk_level_kernel<WIN, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          C::SMEM_BYTES));
-        attr_set[dev] = true;
-    }
-    CUtensorMap tmP, tmQ;
-    int rc = make_image_map(&tmP, a.prev, a.w, a.h_local, a.n_pairs, a.pitch, a.image_stride, C::CH);
-    if (rc) return rc;
-    rc = make_image_map(&tmQ, a.next, a.w, a.h_local, a.n_pairs, a.pitch, a.image_stride, C::CH);
-    if (rc) return rc;
-
-    const int out_rows = a.out_y1 - a.out_y0;
-    const int strips = (a.w + C::TWO - 1) / C::TWO;
-    // Rows per CTA.  The hardware hands CTAs to SMs as slots free up, so a launch takes about
-    // (total row-steps) / SMs plus a ragged tail of roughly half a CTA's lifetime (MIN_BLOCKS CTAs
-    // share an SM, so a CTA lives MIN_BLOCKS times its own row-steps).  Short CTAs shrink the tail,
-    // tall CTAs amortise the 2R+2 halo rows: take the split that minimises the sum.
-    const int n_sm = a.sm_count > 0 ? a.sm_count : 148;
-    const long long cols = (long long)strips * a.n_pairs;
-    const int max_ny = (out_rows + C::CH - 1) / C::CH;
-    int rows_per_block = out_rows;
-    double best = 1e300;
-    for (int ny = 1; ny <= max_ny && ny <= 128; ny++) {
-        int rpb = (out_rows + ny - 1) / ny;
-        rpb = ((rpb + C::SUB - 1) / C::SUB) * C::SUB;
-        const int nb = (out_rows + rpb - 1) / rpb;
-        const double steps = rpb + 2 * C::R + 2 + C::SUB;
-        const double cost = (double)(cols * nb) * steps / n_sm + 0.5 * C::MIN_BLOCKS * steps;
-        if (cost < best * 0.999) {
-            best = cost;
-            rows_per_block = rpb;
-        }
-    }
-    const int nby = (out_rows + rows_per_block - 1) / rows_per_block;
-
-    LkKernelParams p;
-    p.next = a.next;
-    p.pitch = (int)a.pitch;
-    p.image_stride = a.image_stride;
-    p.w = a.w;
-    p.h_local = a.h_local;
-    p.y_off = a.y_off;
-    p.h_global = a.h_global;
-    p.out_y0 = a.out_y0;
-    p.out_y1 = a.out_y1;
-    p.rows_per_block = rows_per_block;
-    p.as_written = (a.warp_mode == OFB_WARP_AS_WRITTEN) ? 1 : 0;
-    p.scale2 = 2.0f * a.flow_scale;
-    p.scale512 = 512.0f * a.flow_scale;
-    p.cum_in = reinterpret_cast<const float2 *>(a.cum_in);
-    p.cum_w = a.cum_w;
-    p.cum_h_global = a.cum_h_global;
-    p.cum_y_off = a.cum_y_off;
-    p.cum_h_local = a.cum_h_local;
-    p.cum_pair_stride = a.cum_pair_stride;
-    p.flow_out = reinterpret_cast<float2 *>(a.flow_out);
-    p.cum_out = reinterpret_cast<float2 *>(a.cum_out);
-    p.flow_pair_stride = a.flow_pair_stride;
-    p.reach_overflow = a.reach_overflow;
-
-    dim3 grid((unsigned)strips, (unsigned)nby, (unsigned)a.n_pairs);
-    lk_level_kernel<WIN, MODE><<<grid, LK_NT, C::SMEM_BYTES, stream>>>(tmP, tmQ, p);
-    OFB_CUDA_TRY(cudaGetLastError());
-    if (launches) ++*launches;
-    return OFB_OK;
-}
-
-template <int WIN> static int launch_mode(const LkLevelArgs &a, cudaStream_t s, unsigned long long *l)
-{
-    if (a.cum_in == nullptr) return launch_one<WIN, 0>(a, s, l);
-    if (a.warp_mode == OFB_WARP_BILINEAR) return launch_one<WIN, 2>(a, s, l);
-    return launch_one<WIN, 1>(a, s, l);
-}
+template <int WIN> int launch_lk_win(const LkLevelArgs &a, cudaStream_t stream, unsigned long long *launches); // lk_win.cu
 
 int launch_lk_level(const LkLevelArgs &a, cudaStream_t stream, unsigned long long *launches)
 {
@@ -145,6 +67,10 @@ int launch_lk_level(const LkLevelArgs &a, cudaStream_t stream, unsigned long lon
         set_error("lk_level: at most 65535 pairs per launch (got %d)", a.n_pairs);
         return OFB_ERR_INVALID;
     }
+    if (a.cum_in && (a.w > 32768 || a.h_global > 32768)) {
+        set_error("lk_level: warped levels are limited to 32768 x 32768 pixels (got %d x %d)", a.w, a.h_global);
+        return OFB_ERR_INVALID;
+    }
     if (a.warp_mode < OFB_WARP_AS_WRITTEN || a.warp_mode > OFB_WARP_BILINEAR) {
         set_error("lk_level: unknown warp mode %d", a.warp_mode);
         return OFB_ERR_INVALID;
@@ -154,15 +80,15 @@ int launch_lk_level(const LkLevelArgs &a, cudaStream_t stream, unsigned long lon
         return OFB_ERR_INVALID;
     }
     switch (a.win) {
-    case 3: return launch_mode<3>(a, stream, launches);
-    case 5: return launch_mode<5>(a, stream, launches);
-    case 7: return launch_mode<7>(a, stream, launches);
-    case 9: return launch_mode<9>(a, stream, launches);
-    case 11: return launch_mode<11>(a, stream, launches);
-    case 13: return launch_mode<13>(a, stream, launches);
-    case 15: return launch_mode<15>(a, stream, launches);
-    case 17: return launch_mode<17>(a, stream, launches);
-    case 19: return launch_mode<19>(a, stream, launches);
+    case 3: return launch_lk_win<3>(a, stream, launches);
+    case 5: return launch_lk_win<5>(a, stream, launches);
+    case 7: return launch_lk_win<7>(a, stream, launches);
+    case 9: return launch_lk_win<9>(a, stream, launches);
+    case 11: return launch_lk_win<11>(a, stream, launches);
+    case 13: return launch_lk_win<13>(a, stream, launches);
+    case 15: return launch_lk_win<15>(a, stream, launches);
+    case 17: return launch_lk_win<17>(a, stream, launches);
+    case 19: return launch_lk_win<19>(a, stream, launches);
     default:
         set_error("lk_level: window %d not supported (odd 3..19)", a.win);
         return OFB_ERR_UNSUPPORTED;

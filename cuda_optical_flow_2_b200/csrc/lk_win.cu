@@ -1,0 +1,97 @@
+// lk_win.cu -- the fused per-level LK kernels of ONE window size (-DLK_WIN=n): grid sizing and the
+// (warp mode, cumulative output) dispatch.  See lk_level.cu for the entry point.
+#include "lk_level.cuh"
+
+#ifndef LK_WIN
+#error "compile with -DLK_WIN=<odd window 3..19>"
+#endif
+
+namespace ofb {
+
+int lk_make_image_map(CUtensorMap *tm, const uint8_t *base, int w, int h, int n, size_t pitch, size_t stride, int box_rows);
+
+template <int WIN, int MODE, bool CUMOUT>
+static int launch_one(const LkLevelArgs &a, cudaStream_t stream, unsigned long long *launches)
+{
+    using C = LkCfg<WIN>;
+    static bool attr_set[64] = {};
+    int dev = 0;
+    OFB_CUDA_TRY(cudaGetDevice(&dev));
+    if (dev < 64 && !attr_set[dev]) {
+        OFB_CUDA_TRY(cudaFuncSetAttribute(lk_level_kernel<WIN, MODE, CUMOUT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          C::SMEM_BYTES));
+        attr_set[dev] = true;
+    }
+    CUtensorMap tmP, tmQ;
+    int rc = lk_make_image_map(&tmP, a.prev, a.w, a.h_local, a.n_pairs, a.pitch, a.image_stride, C::CH);
+    if (rc) return rc;
+    rc = lk_make_image_map(&tmQ, a.next, a.w, a.h_local, a.n_pairs, a.pitch, a.image_stride, C::CH);
+    if (rc) return rc;
+
+    const int out_rows = a.out_y1 - a.out_y0;
+    const int strips = (a.w + C::TWO - 1) / C::TWO;
+    // Rows per CTA.  The hardware hands CTAs to SMs as slots free up, so a launch takes about
+    // (total row-steps) / SMs plus a ragged tail of roughly half a CTA's lifetime (MIN_BLOCKS CTAs
+    // share an SM, so a CTA lives MIN_BLOCKS times its own row-steps).  Short CTAs shrink the tail,
+    // tall CTAs amortise the 2R+2 halo rows: take the split that minimises the sum.
+    const int n_sm = a.sm_count > 0 ? a.sm_count : 148;
+    const long long cols = (long long)strips * a.n_pairs;
+    const int max_ny = (out_rows + C::CH - 1) / C::CH;
+    int rows_per_block = out_rows;
+    double best = 1e300;
+    for (int ny = 1; ny <= max_ny && ny <= 128; ny++) {
+        int rpb = (out_rows + ny - 1) / ny;
+        rpb = ((rpb + C::SUB - 1) / C::SUB) * C::SUB;
+        const int nb = (out_rows + rpb - 1) / rpb;
+        const double steps = rpb + 2 * C::R + 2 + C::SUB;
+        const double cost = (double)(cols * nb) * steps / n_sm + 0.5 * C::MIN_BLOCKS * steps;
+        if (cost < best * 0.999) {
+            best = cost;
+            rows_per_block = rpb;
+        }
+    }
+    const int nby = (out_rows + rows_per_block - 1) / rows_per_block;
+
+    LkKernelParams p;
+    p.next = a.next;
+    p.pitch = (int)a.pitch;
+    p.image_stride = a.image_stride;
+    p.w = a.w;
+    p.h_local = a.h_local;
+    p.y_off = a.y_off;
+    p.h_global = a.h_global;
+    p.out_y0 = a.out_y0;
+    p.out_y1 = a.out_y1;
+    p.rows_per_block = rows_per_block;
+    p.as_written = (a.warp_mode == OFB_WARP_AS_WRITTEN) ? 1 : 0;
+    p.scale2 = 2.0f * a.flow_scale;
+    p.scale512 = 512.0f * a.flow_scale;
+    p.cum_in = reinterpret_cast<const float2 *>(a.cum_in);
+    p.cum_w = a.cum_w;
+    p.cum_h_global = a.cum_h_global;
+    p.cum_y_off = a.cum_y_off;
+    p.cum_h_local = a.cum_h_local;
+    p.cum_pair_stride = a.cum_pair_stride;
+    p.flow_out = reinterpret_cast<float2 *>(a.flow_out);
+    p.cum_out = reinterpret_cast<float2 *>(a.cum_out);
+    p.flow_pair_stride = a.flow_pair_stride;
+    p.reach_overflow = a.reach_overflow;
+
+    dim3 grid((unsigned)strips, (unsigned)nby, (unsigned)a.n_pairs);
+    lk_level_kernel<WIN, MODE, CUMOUT><<<grid, LK_NT, C::SMEM_BYTES, stream>>>(tmP, tmQ, p);
+    OFB_CUDA_TRY(cudaGetLastError());
+    if (launches) ++*launches;
+    return OFB_OK;
+}
+
+template <int WIN> int launch_lk_win(const LkLevelArgs &a, cudaStream_t s, unsigned long long *l)
+{
+    const bool co = a.cum_out != nullptr;
+    if (a.cum_in == nullptr) return co ? launch_one<WIN, 0, true>(a, s, l) : launch_one<WIN, 0, false>(a, s, l);
+    if (a.warp_mode == OFB_WARP_BILINEAR) return co ? launch_one<WIN, 2, true>(a, s, l) : launch_one<WIN, 2, false>(a, s, l);
+    return co ? launch_one<WIN, 1, true>(a, s, l) : launch_one<WIN, 1, false>(a, s, l);
+}
+
+template int launch_lk_win<LK_WIN>(const LkLevelArgs &a, cudaStream_t s, unsigned long long *l);
+
+} // namespace ofb
