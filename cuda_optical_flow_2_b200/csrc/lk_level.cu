@@ -21,9 +21,9 @@ PFN_encodeTiled get_encode_tiled()
     return fn;
 }
 
-// u8 image batch as a 3-D tensor (x, y, image); box = LK_TILE_W x rows x 1; OOB reads give 0.
-int lk_make_image_map(CUtensorMap *tm, const uint8_t *base, int w, int h, int n, size_t pitch, size_t stride,
-                          int box_rows)
+// u8 image batch as a 3-D tensor (x, y, image); box = box_w x box_rows x 1; OOB reads give 0.
+int lk_make_image_map(CUtensorMap *tm, const uint8_t *base, int w, int h, int n, size_t pitch, size_t stride, int box_w,
+                      int box_rows)
 {
     PFN_encodeTiled enc = get_encode_tiled();
     if (!enc) {
@@ -38,7 +38,7 @@ int lk_make_image_map(CUtensorMap *tm, const uint8_t *base, int w, int h, int n,
     cuuint64_t dims[3] = {(cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n};
     cuuint64_t strides[2] = {(cuuint64_t)pitch, (cuuint64_t)(n > 1 ? stride : pitch * (size_t)h)};
     if (strides[1] & 15) strides[1] = (strides[1] + 15) & ~(cuuint64_t)15;
-    cuuint32_t box[3] = {(cuuint32_t)LK_TILE_W, (cuuint32_t)box_rows, 1};
+    cuuint32_t box[3] = {(cuuint32_t)box_w, (cuuint32_t)box_rows, 1};
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<uint8_t *>(base), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,

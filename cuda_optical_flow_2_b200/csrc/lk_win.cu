@@ -8,7 +8,8 @@
 
 namespace ofb {
 
-int lk_make_image_map(CUtensorMap *tm, const uint8_t *base, int w, int h, int n, size_t pitch, size_t stride, int box_rows);
+int lk_make_image_map(CUtensorMap *tm, const uint8_t *base, int w, int h, int n, size_t pitch, size_t stride, int box_w,
+                      int box_rows);
 
 template <int WIN, int MODE, bool CUMOUT>
 static int launch_one(const LkLevelArgs &a, cudaStream_t stream, unsigned long long *launches)
@@ -23,9 +24,11 @@ static int launch_one(const LkLevelArgs &a, cudaStream_t stream, unsigned long l
         attr_set[dev] = true;
     }
     CUtensorMap tmP, tmQ;
-    int rc = lk_make_image_map(&tmP, a.prev, a.w, a.h_local, a.n_pairs, a.pitch, a.image_stride, C::CH);
+    int rc = lk_make_image_map(&tmP, a.prev, a.w, a.h_local, a.n_pairs, a.pitch, a.image_stride, LK_TILE_W, C::CH);
     if (rc) return rc;
-    rc = lk_make_image_map(&tmQ, a.next, a.w, a.h_local, a.n_pairs, a.pitch, a.image_stride, C::CH);
+    // next: the same box as prev on the coarsest level, the window with margin on bilinearly warped levels
+    rc = lk_make_image_map(&tmQ, a.next, a.w, a.h_local, a.n_pairs, a.pitch, a.image_stride, MODE == 2 ? LK_NTW : LK_TILE_W,
+                           MODE == 2 ? C::NTH : C::CH);
     if (rc) return rc;
 
     const int out_rows = a.out_y1 - a.out_y0;
