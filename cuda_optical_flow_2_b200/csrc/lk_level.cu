@@ -50,6 +50,35 @@ int lk_make_image_map(CUtensorMap *tm, const uint8_t *base, int w, int h, int n,
     return OFB_OK;
 }
 
+// float2 flow field batch as a 3-D tensor of floats (2*w, h, pair); box = 2*box_w x box_rows x 1; OOB reads give 0.
+// Returns OFB_OK with *usable = 0 when the layout cannot have a tensor map (base, row or pair stride not a
+// multiple of 16 bytes: odd widths); the kernel then copies its tiles itself.
+int lk_make_flow_map(CUtensorMap *tm, const float *base, int w, int h, int n, size_t pair_stride_vec, int box_w, int box_rows,
+                     int *usable)
+{
+    *usable = 0;
+    PFN_encodeTiled enc = get_encode_tiled();
+    if (!enc) {
+        set_error("cuTensorMapEncodeTiled is not available from this driver");
+        return OFB_ERR_CUDA;
+    }
+    const size_t row_bytes = (size_t)w * 8, pair_bytes = pair_stride_vec * 8;
+    if ((reinterpret_cast<uintptr_t>(base) & 15) || (row_bytes & 15) || (n > 1 && (pair_bytes & 15))) return OFB_OK;
+    cuuint64_t dims[3] = {(cuuint64_t)(2 * w), (cuuint64_t)h, (cuuint64_t)n};
+    cuuint64_t strides[2] = {(cuuint64_t)row_bytes, (cuuint64_t)(n > 1 ? pair_bytes : row_bytes * (size_t)h)};
+    cuuint32_t box[3] = {(cuuint32_t)(2 * box_w), (cuuint32_t)box_rows, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float *>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled (flow) failed with CUresult %d (w %d h %d n %d)", (int)r, w, h, n);
+        return OFB_ERR_CUDA;
+    }
+    *usable = 1;
+    return OFB_OK;
+}
+
 template <int WIN> int launch_lk_win(const LkLevelArgs &a, cudaStream_t stream, unsigned long long *launches); // lk_win.cu
 
 int launch_lk_level(const LkLevelArgs &a, cudaStream_t stream, unsigned long long *launches)

@@ -2,6 +2,8 @@
 // (warp mode, cumulative output) dispatch.  See lk_level.cu for the entry point.
 #include "lk_level.cuh"
 
+#include <cstdlib>
+
 #ifndef LK_WIN
 #error "compile with -DLK_WIN=<odd window 3..19>"
 #endif
@@ -10,6 +12,8 @@ namespace ofb {
 
 int lk_make_image_map(CUtensorMap *tm, const uint8_t *base, int w, int h, int n, size_t pitch, size_t stride, int box_w,
                       int box_rows);
+int lk_make_flow_map(CUtensorMap *tm, const float *base, int w, int h, int n, size_t pair_stride_vec, int box_w, int box_rows,
+                     int *usable);
 
 template <int WIN, int MODE, bool CUMOUT>
 static int launch_one(const LkLevelArgs &a, cudaStream_t stream, unsigned long long *launches)
@@ -30,6 +34,13 @@ static int launch_one(const LkLevelArgs &a, cudaStream_t stream, unsigned long l
     rc = lk_make_image_map(&tmQ, a.next, a.w, a.h_local, a.n_pairs, a.pitch, a.image_stride, MODE == 2 ? LK_NTW : LK_TILE_W,
                            MODE == 2 ? C::NTH : C::CH);
     if (rc) return rc;
+    // coarser cumulative flow of bilinearly warped levels: tiles of NBR x LK_CTW vectors
+    CUtensorMap tmC = tmP;
+    int cum_tma = 0;
+    if (MODE == 2) {
+        rc = lk_make_flow_map(&tmC, a.cum_in, a.cum_w, a.cum_h_local, a.n_pairs, a.cum_pair_stride, LK_CTW, C::NBR, &cum_tma);
+        if (rc) return rc;
+    }
 
     const int out_rows = a.out_y1 - a.out_y0;
     const int strips = (a.w + C::TWO - 1) / C::TWO;
@@ -43,15 +54,21 @@ static int launch_one(const LkLevelArgs &a, cudaStream_t stream, unsigned long l
     int rows_per_block = out_rows;
     double best = 1e300;
     for (int ny = 1; ny <= max_ny && ny <= 128; ny++) {
-        int rpb = (out_rows + ny - 1) / ny;
-        rpb = ((rpb + C::SUB - 1) / C::SUB) * C::SUB;
+        const int rpb = (out_rows + ny - 1) / ny;
         const int nb = (out_rows + rpb - 1) / rpb;
-        const double steps = rpb + 2 * C::R + 2 + C::SUB;
+        // rows a CTA processes: its outputs plus the 2R+2 halo rows (+1 for the even first row), rounded up to
+        // whole sub-chunks by the V/H phases and to whole chunks by the gather (about a quarter of the work)
+        const int need = rpb + 2 * C::R + 3;
+        const double steps = 0.75 * ((need + C::SUB - 1) / C::SUB * C::SUB) + 0.25 * ((need + C::CH - 1) / C::CH * C::CH);
         const double cost = (double)(cols * nb) * steps / n_sm + 0.5 * C::MIN_BLOCKS * steps;
         if (cost < best * 0.999) {
             best = cost;
             rows_per_block = rpb;
         }
+    }
+    if (const char *dbg = getenv("OFB_LK_ROWS")) { // developer override for experiments
+        const int v = atoi(dbg);
+        if (v > 0) rows_per_block = v < out_rows ? v : out_rows;
     }
     const int nby = (out_rows + rows_per_block - 1) / rows_per_block;
 
@@ -79,9 +96,10 @@ static int launch_one(const LkLevelArgs &a, cudaStream_t stream, unsigned long l
     p.cum_out = reinterpret_cast<float2 *>(a.cum_out);
     p.flow_pair_stride = a.flow_pair_stride;
     p.reach_overflow = a.reach_overflow;
+    p.cum_tma = cum_tma;
 
     dim3 grid((unsigned)strips, (unsigned)nby, (unsigned)a.n_pairs);
-    lk_level_kernel<WIN, MODE, CUMOUT><<<grid, LK_NT, C::SMEM_BYTES, stream>>>(tmP, tmQ, p);
+    lk_level_kernel<WIN, MODE, CUMOUT><<<grid, LK_NT, C::SMEM_BYTES, stream>>>(tmP, tmQ, tmC, p);
     OFB_CUDA_TRY(cudaGetLastError());
     if (launches) ++*launches;
     return OFB_OK;
