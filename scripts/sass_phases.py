@@ -7,7 +7,7 @@ import subprocess
 import sys
 
 obj, win, mode, co = sys.argv[1], sys.argv[2], sys.argv[3], sys.argv[4]
-fun = f"_ZN3ofb15lk_level_kernelILi{win}ELi{mode}ELb{co}EEEv14CUtensorMap_stS1_NS_14LkKernelParamsE"
+fun = f"_ZN3ofb15lk_level_kernelILi{win}ELi{mode}ELb{co}EEEv14CUtensorMap_stS1_S1_NS_14LkKernelParamsE"
 out = subprocess.run(["cuobjdump", "-sass", "-fun", fun, obj], capture_output=True, text=True).stdout
 ins = []
 for line in out.splitlines():
