@@ -6,7 +6,7 @@ sharding and row-strip partitioning over torch.distributed).  There is no CPU im
 """
 from ._lib import (LIB_PATH, MAX_LEVELS, MAX_WINDOW, WARP_AS_WRITTEN, WARP_BILINEAR, WARP_NEAREST, OfbError,
                    OfbParams)
-from .api import REFERENCE_WINDOW, Context, align_up, planar_to_device
+from .api import REFERENCE_WINDOW, Context, align_up, planar_to_device, write_flo
 
 __all__ = ["Context", "OfbError", "OfbParams", "WARP_AS_WRITTEN", "WARP_NEAREST", "WARP_BILINEAR", "MAX_LEVELS",
-           "MAX_WINDOW", "REFERENCE_WINDOW", "LIB_PATH", "align_up", "planar_to_device"]
+           "MAX_WINDOW", "REFERENCE_WINDOW", "LIB_PATH", "align_up", "planar_to_device", "write_flo"]

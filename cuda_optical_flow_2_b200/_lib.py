@@ -72,6 +72,9 @@ SIGNATURES = {
     "ofb_stream_create": (C.c_int, [_vp, C.POINTER(OfbParams), C.c_int, C.c_double, C.c_double, C.POINTER(_vp)]),
     "ofb_stream_push_bgr_host": (C.c_int, [_vp, u8p, C.POINTER(f32p), f32p, i32p]),
     "ofb_stream_destroy": (C.c_int, [_vp]),
+    "ofb_compose_flow_host": (C.c_int, [_vp, C.POINTER(f32p), C.c_int, C.c_int, C.c_int, C.c_int, f32p]),
+    "ofb_flow_arrows_host": (C.c_int, [_vp, C.POINTER(f32p), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, i32p, C.c_int, i32p]),
+    "ofb_write_flo": (C.c_int, [C.c_char_p, f32p, C.c_int, C.c_int]),
     "ofb_host_alloc": (C.c_int, [C.POINTER(_vp), _sz]),
     "ofb_host_free": (C.c_int, [_vp]),
 }

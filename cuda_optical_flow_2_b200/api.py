@@ -12,6 +12,7 @@ torch CUDA tensors only as owners of device memory; torch does none of the arith
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Optional, Sequence
 
 import numpy as np
@@ -151,6 +152,25 @@ class Context:
             raise ValueError("optFlowPyramid[level] must be (h, w, 2) float32")
         ptrs = (L.f32p * (level + 1))(*[a.ctypes.data_as(L.f32p) for a in arrs])
         L.check(self._lib.ofb_inverse_matrix_f32_host(self._h, *[s.ctypes.data_as(L.f32p) for s in sums], ptrs, level, w, h))
+
+    # ---- flow composition and export: the headless part of visualizeFlowField (main.cu:114-174) ----
+    def compose_flow(self, flow_pyramid: Sequence[np.ndarray], w: int, h: int, levels: int, level: int = 0) -> np.ndarray:
+        """Total flow of `level` from the residual pyramid (composition rule main.cu:136-147)."""
+        flows = [_f32(f) for f in flow_pyramid]
+        out = np.empty((h >> level, w >> level, 2), np.float32)
+        L.check(self._lib.ofb_compose_flow_host(self._h, _ptrs(flows, L.f32p), w, h, levels, level, out.ctypes.data_as(L.f32p)))
+        return out
+
+    def flow_arrows(self, flow_pyramid: Sequence[np.ndarray], w: int, h: int, levels: int, level: int, arrow_res: int) -> np.ndarray:
+        """(n, 4) int32 array of (x0, y0, x1, y1): the arrows main.cu:125-171 draws."""
+        flows = [_f32(f) for f in flow_pyramid]
+        cap = (arrow_res + 2) * ((h >> level) // max((w >> level) // arrow_res, 1) + 2)
+        buf = np.empty((cap, 4), np.int32)
+        n = C.c_int(0)
+        L.check(self._lib.ofb_flow_arrows_host(self._h, _ptrs(flows, L.f32p), w, h, levels, level, arrow_res,
+                                               buf.ctypes.data_as(L.i32p), cap, C.byref(n)))
+        assert n.value <= cap
+        return buf[: n.value].copy()
 
     def grayscale_avg(self, src: np.ndarray, h: int, w: int) -> np.ndarray:
         """gpu::grayscale_avg(src, dest, h, w) (OptFlowGpu.cu:75; height before width like the reference)."""
@@ -317,6 +337,12 @@ class FrameStream:
             self.close()
         except Exception:
             pass
+
+
+def write_flo(path: str, flow: np.ndarray) -> None:
+    """Middlebury .flo file of an (h, w, 2) float32 flow field."""
+    f = _f32(flow)
+    L.check(L.load().ofb_write_flo(os.fsencode(path), f.ctypes.data_as(L.f32p), f.shape[1], f.shape[0]))
 
 
 def planar_to_device(imgs: np.ndarray, device="cuda:0"):

@@ -68,6 +68,8 @@ int main(int argc, char **argv)
 {
     int w = 640, h = 480, levels = 4, frames = 8, win = 19, warp = OFB_WARP_AS_WRITTEN, batch = 0;
     float step = 1.0f;
+    const char *flo = nullptr; // --flo PREFIX: write PREFIX_<frame>.flo
+    int arrow_res = 0;         // --arrows RES: count the arrows of visualizeFlowField(..., arrowRes)
     for (int i = 1; i < argc; i++) {
         auto arg = [&](const char *n) { return !strcmp(argv[i], n) && i + 1 < argc; };
         if (arg("--w")) w = atoi(argv[++i]);
@@ -78,8 +80,10 @@ int main(int argc, char **argv)
         else if (arg("--warp")) warp = atoi(argv[++i]);
         else if (arg("--step")) step = (float)atof(argv[++i]);
         else if (arg("--batch")) batch = atoi(argv[++i]);
+        else if (arg("--flo")) flo = argv[++i];
+        else if (arg("--arrows")) arrow_res = atoi(argv[++i]);
         else {
-            fprintf(stderr, "usage: %s [--w W --h H --levels L --frames N --win WIN --warp 0|1|2 --step PX --batch N]\n", argv[0]);
+            fprintf(stderr, "usage: %s [--w W --h H --levels L --frames N --win WIN --warp 0|1|2 --step PX --batch N --flo PREFIX --arrows RES]\n", argv[0]);
             return 2;
         }
     }
@@ -124,6 +128,7 @@ int main(int argc, char **argv)
     alloc_pyramid<unsigned char, 3>(&pyramid, w, h, levels);
     alloc_pyramid<float, 2>(&flow_pyramid, w, h, levels);
 
+    std::vector<float> total((size_t)w * h * 2);
     make_frame_c3(prev_pyramid[0], w, h, 0, 0, 8, 1234);
     gpu::gauss_pyramid(prev_pyramid, w, h, levels, GAUS_KERNEL_3x3, 3, 3); // main.cu:209
     for (int f = 1; f <= frames; f++) {
@@ -134,23 +139,37 @@ int main(int argc, char **argv)
             gpu::calc_opt_flow(prev_pyramid[k], pyramid[k], w >> k, h >> k, flow_pyramid, k, levels);
         auto t1 = std::chrono::steady_clock::now();
         if (gpu::last_status() != OFB_OK) return 1;
-        // composition at level 0, main.cu:136-147
+        // composition at level 0 (main.cu:136-147) on the device, in place of visualizeFlowField's per-arrow loop
+        if (ofb_compose_flow_host(gpu::default_context(), flow_pyramid, w, h, levels, 0, total.data())) {
+            fprintf(stderr, "ofb_compose_flow_host: %s\n", ofb_last_error());
+            return 1;
+        }
         std::vector<float> us, vs;
-        for (int i = 0; i < h; i += 7)
-            for (int j = 0; j < w; j += 7) {
-                float u = 0, v = 0;
-                for (int k = levels - 1; k >= 0; k--) {
-                    const size_t pos = (size_t)(i >> k) * (w >> k) + (j >> k);
-                    u += (float)(1 << k) * flow_pyramid[k][pos * 2];
-                    v += (float)(1 << k) * flow_pyramid[k][pos * 2 + 1];
-                }
-                if (std::isfinite(u) && std::isfinite(v)) {
-                    us.push_back(u);
-                    vs.push_back(v);
-                }
+        for (size_t i = 0; i < total.size(); i += 2 * 49)
+            if (std::isfinite(total[i]) && std::isfinite(total[i + 1])) {
+                us.push_back(total[i]);
+                vs.push_back(total[i + 1]);
             }
         printf("frame %d: %.2f ms, median composed flow (u,v) = (%.3f, %.3f) [units of 15/8 px, SURVEY Q1]\n", f,
                std::chrono::duration<double, std::milli>(t1 - t0).count(), median(us), median(vs));
+        if (flo) { // export instead of imshow: the dense total flow as a Middlebury .flo file
+            char path[1024];
+            snprintf(path, sizeof path, "%s_%04d.flo", flo, f);
+            if (ofb_write_flo(path, total.data(), w, h)) {
+                fprintf(stderr, "ofb_write_flo: %s\n", ofb_last_error());
+                return 1;
+            }
+        }
+        if (arrow_res > 0) { // the arrows main.cu:125-171 would draw
+            std::vector<int> arrows((size_t)4 * (arrow_res + 2) * (arrow_res + 2) * 4);
+            int n = 0;
+            if (ofb_flow_arrows_host(gpu::default_context(), flow_pyramid, w, h, levels, 0, arrow_res, arrows.data(),
+                                     (int)(arrows.size() / 4), &n)) {
+                fprintf(stderr, "ofb_flow_arrows_host: %s\n", ofb_last_error());
+                return 1;
+            }
+            printf("  %d arrows on a grid of step %d px\n", n, w / arrow_res);
+        }
         unsigned char **swap = prev_pyramid; // main.cu:270-272
         prev_pyramid = pyramid;
         pyramid = swap;

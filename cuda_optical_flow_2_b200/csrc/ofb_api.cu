@@ -919,6 +919,119 @@ int ofb_bilateral_planar_device(ofb_ctx *c, const uint8_t *gray_d, size_t pitch,
                             static_cast<cudaStream_t>(stream), &c->launches);
 }
 
+// ---- flow composition and export (the headless part of main.cu:114-174) ----------------------
+
+int ofb_compose_flow_host(ofb_ctx *c, float *const *flow_pyramid_h, int w, int h, int levels, int level, float *total_h)
+{
+    OFB_CHECK_CTX(c);
+    if (!flow_pyramid_h || !total_h || w < 1 || h < 1 || levels < 1 || levels > OFB_MAX_LEVELS || level < 0 || level >= levels ||
+        (w >> (levels - 1)) < 1 || (h >> (levels - 1)) < 1) {
+        set_error("compose_flow: bad arguments (w %d h %d levels %d level %d)", w, h, levels, level);
+        return OFB_ERR_INVALID;
+    }
+    for (int k = level; k < levels; k++)
+        if (!flow_pyramid_h[k]) {
+            set_error("compose_flow: flow_pyramid[%d] is NULL", k);
+            return OFB_ERR_INVALID;
+        }
+    OFB_GUARD(c);
+    // device: residual flow of levels level..levels-1 and two ping-pong cumulative buffers of the finest size
+    Carver cv;
+    size_t off_res[OFB_MAX_LEVELS];
+    for (int k = level; k < levels; k++) off_res[k] = cv.take((size_t)(w >> k) * (h >> k) * 8);
+    const size_t n0 = (size_t)(w >> level) * (h >> level) * 8;
+    const size_t off_a = cv.take(n0), off_b = cv.take(n0);
+    int rc = ws_reserve(c, cv.off);
+    if (rc) return rc;
+    cudaStream_t st = c->stream;
+    for (int k = level; k < levels; k++)
+        OFB_CUDA_TRY(cudaMemcpyAsync(c->ws + off_res[k], flow_pyramid_h[k], (size_t)(w >> k) * (h >> k) * 8,
+                                     cudaMemcpyHostToDevice, st));
+    // coarse to fine: cum_{L-1} = flow_{L-1}; cum_k = 2*cum_{k+1}[i>>1][j>>1] + flow_k
+    const float *cum = nullptr;
+    size_t cur = off_a, other = off_b;
+    for (int k = levels - 1; k >= level; k--) {
+        rc = launch_compose_cum(reinterpret_cast<const float *>(c->ws + off_res[k]), cum, w >> k, h >> k, 1,
+                                reinterpret_cast<float *>(c->ws + cur), st, &c->launches);
+        if (rc) return rc;
+        cum = reinterpret_cast<const float *>(c->ws + cur);
+        std::swap(cur, other);
+    }
+    OFB_CUDA_TRY(cudaMemcpyAsync(total_h, cum, n0, cudaMemcpyDeviceToHost, st));
+    OFB_CUDA_TRY(cudaStreamSynchronize(st));
+    return OFB_OK;
+}
+
+int ofb_flow_arrows_host(ofb_ctx *c, float *const *flow_pyramid_h, int w, int h, int levels, int level, int arrow_res,
+                         int *arrows_xyxy, int max_arrows, int *n_arrows)
+{
+    OFB_CHECK_CTX(c);
+    if (!n_arrows || arrow_res < 1 || max_arrows < 0 || (max_arrows > 0 && !arrows_xyxy)) {
+        set_error("flow_arrows: bad arguments");
+        return OFB_ERR_INVALID;
+    }
+    if (level < 0 || level >= levels || w < 1 || h < 1) {
+        set_error("flow_arrows: bad geometry (w %d h %d levels %d level %d)", w, h, levels, level);
+        return OFB_ERR_INVALID;
+    }
+    const int wl = w >> level, hl = h >> level;
+    const int step = wl / arrow_res; // main.cu:124
+    if (step < 1) {
+        set_error("flow_arrows: arrow_res %d exceeds the level width %d", arrow_res, wl);
+        return OFB_ERR_INVALID;
+    }
+    std::vector<float> total((size_t)wl * hl * 2);
+    int rc = ofb_compose_flow_host(c, flow_pyramid_h, w, h, levels, level, total.data());
+    if (rc) return rc;
+    int n = 0;
+    for (int i = 0; i < hl; i += step)
+        for (int j = 0; j < wl; j += step) {
+            float u = total[((size_t)i * wl + j) * 2], v = total[((size_t)i * wl + j) * 2 + 1];
+            // main.cu:150-157: clamp to one grid step; NaN compares false and passes through, as in the reference
+            if (u > step) u = (float)step;
+            else if (u < -step) u = (float)-step;
+            if (v > step) v = (float)step;
+            else if (v < -step) v = (float)-step;
+            // main.cu:159-160 casts float to int; the result is undefined there for NaN (x86 gives INT_MIN, which the
+            // sign test then drops): defined here as "no arrow"
+            if (u != u || v != v) continue;
+            const int ni = (int)(v + (float)i), nj = (int)(u + (float)j);
+            if (ni < 0 || nj < 0) continue; // main.cu:163
+            if (n < max_arrows) {
+                arrows_xyxy[4 * n + 0] = j;
+                arrows_xyxy[4 * n + 1] = i;
+                arrows_xyxy[4 * n + 2] = nj;
+                arrows_xyxy[4 * n + 3] = ni;
+            }
+            n++;
+        }
+    *n_arrows = n;
+    return OFB_OK;
+}
+
+int ofb_write_flo(const char *path, const float *flow_h, int w, int h)
+{
+    if (!path || !flow_h || w < 1 || h < 1) {
+        set_error("write_flo: bad arguments");
+        return OFB_ERR_INVALID;
+    }
+    FILE *f = fopen(path, "wb");
+    if (!f) {
+        set_error("write_flo: cannot open %s", path);
+        return OFB_ERR_INVALID;
+    }
+    const float tag = 202021.25f; // "PIEH"
+    const int32_t dims[2] = {w, h};
+    bool ok = fwrite(&tag, 4, 1, f) == 1 && fwrite(dims, 4, 2, f) == 2 &&
+              fwrite(flow_h, 8, (size_t)w * h, f) == (size_t)w * h;
+    ok = (fclose(f) == 0) && ok;
+    if (!ok) {
+        set_error("write_flo: short write to %s", path);
+        return OFB_ERR_INVALID;
+    }
+    return OFB_OK;
+}
+
 } // extern "C"
 
 // One frame sequence: two device-resident planar pyramids that swap roles every frame (main.cu:270-272).

@@ -193,6 +193,22 @@ int ofb_stream_push_bgr_host(ofb_stream *s, const unsigned char *frame_bgr, floa
                              float *total_flow_h, int *has_flow);
 int ofb_stream_destroy(ofb_stream *s);
 
+/* ---- flow composition and export: the headless part of visualizeFlowField (main.cu:114-174) --------------------
+ * flow_pyramid_h[k]: residual flow of level k, (h>>k)*(w>>k)*2 floats, as gpu::calc_opt_flow leaves it
+ * (main.cu:95-104, 256-262); only levels level..levels-1 are read.
+ *
+ * ofb_compose_flow_host: total_h[(i*(w>>level)+j)*2 + {0,1}] = sum_{k=levels-1..level} 2^(k-level) *
+ *   flow_k[(i>>(k-level))*(w>>k) + (j>>(k-level))]  (main.cu:136-147, coarse to fine in float, bit for bit).
+ * ofb_flow_arrows_host: the arrows main.cu:125-171 would draw: grid step (w>>level)/arrow_res, total flow clamped
+ *   to +-step, end point truncated to int, arrows with a negative end point dropped.  arrows_xyxy receives up to
+ *   max_arrows quadruples (x0, y0, x1, y1) in level pixels; *n_arrows is the full count.
+ * ofb_write_flo: Middlebury .flo file (tag 202021.25f, int32 w, int32 h, w*h interleaved (u,v) floats): the file
+ *   form of what the reference only shows on screen. */
+int ofb_compose_flow_host(ofb_ctx *ctx, float *const *flow_pyramid_h, int w, int h, int levels, int level, float *total_h);
+int ofb_flow_arrows_host(ofb_ctx *ctx, float *const *flow_pyramid_h, int w, int h, int levels, int level, int arrow_res,
+                         int *arrows_xyxy, int max_arrows, int *n_arrows);
+int ofb_write_flo(const char *path, const float *flow_h, int w, int h);
+
 /* Pinned host memory helpers for callers without a CUDA runtime of their own. */
 int ofb_host_alloc(void **ptr, size_t bytes);
 int ofb_host_free(void *ptr);

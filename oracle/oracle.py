@@ -314,3 +314,57 @@ def ref_gpu_gauss_pyramid_c3(img0_c3: np.ndarray, levels: int) -> list[np.ndarra
     pyr = [np.ascontiguousarray(img0_c3, np.uint8)] + [np.zeros((h >> k, w >> k, 3), np.uint8) for k in range(1, levels)]
     ref().ref_gpu_gauss_pyramid(_ptr_array(pyr, _u8p), w, h, levels)
     return pyr
+
+
+# ---- flow composition and arrows, literal restatement of main.cu:114-174 (numpy) ----------------
+def compose_total(flows, level: int = 0) -> np.ndarray:
+    """main.cu:136-147: for every pixel of `level`, u = v = 0 (float); for k = levels-1 .. level:
+    u += (double)(1 << (k-level)) * flow_k[(i >> (k-level)) * (w >> (k-level)) + (j >> (k-level))], stored back to
+    float each time.  Indices past a coarser level (odd sizes; the reference reads out of bounds there) are
+    clamped to its last row / column."""
+    levels = len(flows)
+    h, w = flows[level].shape[:2]
+    ii, jj = np.meshgrid(np.arange(h), np.arange(w), indexing="ij")
+    tot = np.zeros((h, w, 2), np.float32)
+    with np.errstate(invalid="ignore", over="ignore"):
+        for k in range(levels - 1, level - 1, -1):
+            sc = k - level
+            fk = flows[k]
+            yi = np.minimum(ii >> sc, fk.shape[0] - 1)
+            xi = np.minimum(jj >> sc, fk.shape[1] - 1)
+            tot = (tot.astype(np.float64) + np.float64(1 << sc) * fk[yi, xi].astype(np.float64)).astype(np.float32)
+    return tot
+
+
+def flow_arrows(flows, level: int, arrow_res: int) -> np.ndarray:
+    """main.cu:124-171 without the drawing: (n, 4) int32 (x0, y0, x1, y1)."""
+    h, w = flows[level].shape[:2]
+    step = w // arrow_res
+    tot = compose_total(flows, level)
+    out = []
+    for i in range(0, h, step):
+        for j in range(0, w, step):
+            u, v = np.float32(tot[i, j, 0]), np.float32(tot[i, j, 1])
+            if u > step:
+                u = np.float32(step)
+            elif u < -step:
+                u = np.float32(-step)
+            if v > step:
+                v = np.float32(step)
+            elif v < -step:
+                v = np.float32(-step)
+            if np.isnan(u) or np.isnan(v):  # (int)NaN is undefined in the reference; x86 yields INT_MIN -> dropped
+                continue
+            ni, nj = int(np.float32(v + np.float32(i))), int(np.float32(u + np.float32(j)))
+            if ni < 0 or nj < 0:
+                continue
+            out.append((j, i, nj, ni))
+    return np.array(out, np.int32).reshape(-1, 4)
+
+
+def read_flo(path: str) -> np.ndarray:
+    with open(path, "rb") as f:
+        tag = np.frombuffer(f.read(4), np.float32)[0]
+        w, h = np.frombuffer(f.read(8), np.int32)
+        assert tag == np.float32(202021.25)
+        return np.frombuffer(f.read(), np.float32).reshape(h, w, 2).copy()
