@@ -175,6 +175,50 @@ class DistTransport(Transport):
                 req.wait()
 
 
+class GatherTransport(Transport):
+    """Halo exchange as ONE all-gather per exchange: every rank contributes two fixed-size slots (its message to
+    the rank below, its message to the rank above) and reads its neighbours' slots.  More bytes than point-to-point
+    (world x 2 slots, still a few MB over NVSwitch) but a single collective of constant shape per exchange, which
+    -- unlike grouped send/recv -- captures cleanly in a CUDA graph, so a whole pair (kernels + exchanges) replays
+    without host work.  Only adjacent ranks may talk (halo smaller than a strip).  Slot sizes are agreed on with an
+    all-reduce the first time each exchange of a step is seen; `begin_step()` restarts the numbering."""
+
+    def __init__(self, rank: int, world: int, device, group=None):
+        import torch
+        import torch.distributed as dist
+
+        self.torch, self.dist, self.group = torch, dist, group
+        self.rank, self.world, self.dev = rank, world, device
+        self._idx, self._bufs = 0, []
+
+    def begin_step(self) -> None:
+        self._idx = 0
+
+    def exchange(self, sends, recvs) -> None:
+        torch, dist = self.torch, self.dist
+        i = self._idx
+        self._idx += 1
+        if i >= len(self._bufs):  # first step only (never under graph capture): agree on the slot size
+            n = max([t.numel() * t.element_size() for _, t in list(sends) + list(recvs)] + [16])
+            tt = torch.tensor([n], dtype=torch.int64, device=self.dev)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX, group=self.group)
+            n = (int(tt.item()) + 15) // 16 * 16
+            self._bufs.append((torch.zeros((2, n), dtype=torch.uint8, device=self.dev),
+                               torch.zeros((self.world, 2, n), dtype=torch.uint8, device=self.dev)))
+        out, inn = self._bufs[i]
+        for peer, t in sends:
+            if abs(peer - self.rank) != 1:
+                raise ValueError("GatherTransport: only adjacent ranks exchange halos")
+            b = t.reshape(-1).view(torch.uint8)
+            out[0 if peer < self.rank else 1, : b.numel()].copy_(b)
+        dist.all_gather_into_tensor(inn.view(-1), out.view(-1), group=self.group)
+        for peer, t in recvs:
+            if abs(peer - self.rank) != 1:
+                raise ValueError("GatherTransport: only adjacent ranks exchange halos")
+            nb = t.numel() * t.element_size()
+            t.copy_(inn[peer, 1 if peer < self.rank else 0, :nb].view(t.dtype).view(t.shape))
+
+
 class StripRunner:
     """One rank's share of a row-strip solve.  All tensors are torch tensors on this rank's device."""
 
@@ -186,6 +230,9 @@ class StripRunner:
             raise ValueError("OFB_WARP_AS_WRITTEN needs pixel (0,0) of every coarser level: not available on strips")
         self.torch, self.ctx, self.plan, self.rank, self.tp, self.dev = torch, ctx, plan, rank, transport, device
         self.warp_mode, self.flow_scale = warp_mode, flow_scale
+        # CUDA stream handle the kernels are enqueued on (0 = the default stream).  `use_current_stream()`
+        # re-reads torch's current stream, which is what CUDA-graph capture of `step()` needs.
+        self.stream = 0
         self.strips = [plan.level(k, rank) for k in range(plan.levels)]
         self.pitch = [align_up(s.w, 64) for s in self.strips]
         z = lambda rows, cols, dt: torch.zeros((rows, cols), dtype=dt, device=device)
@@ -198,6 +245,18 @@ class StripRunner:
         self.cum_in = [torch.zeros((max(s.cy1 - s.cy0, 1), s.w >> 1, 2), dtype=torch.float32, device=device)
                        for s in self.strips]
         self.overflow = torch.zeros(1, dtype=torch.int32, device=device)
+
+    def use_current_stream(self) -> None:
+        self.stream = self.torch.cuda.current_stream(self.dev).cuda_stream
+
+    def step(self, prev_rows, next_rows) -> None:
+        """One pair, everything asynchronous on the stream (no host synchronisation): capturable in a CUDA
+        graph together with its NCCL halo exchanges.  Call check_overflow() afterwards (it synchronises)."""
+        if hasattr(self.tp, "begin_step"):
+            self.tp.begin_step()
+        self.load_level0(prev_rows, next_rows)
+        self.build_pyramid()
+        self.solve(check=False)
 
     # -- data in ---------------------------------------------------------------------------------
     def load_level0(self, prev_rows, next_rows) -> None:
@@ -278,7 +337,8 @@ class StripRunner:
     def pyr_down_own(self, k: int) -> None:
         s, d = self.strips[k], self.strips[k + 1]
         for buf in (self.prev, self.next):
-            self.ctx.pyr_down_strip_device(buf[k], s.w, s.by0, buf[k + 1][d.y0 - d.by0:d.y1 - d.by0], d.y0, d.y1)
+            self.ctx.pyr_down_strip_device(buf[k], s.w, s.by0, buf[k + 1][d.y0 - d.by0:d.y1 - d.by0], d.y0, d.y1,
+                                           stream=self.stream)
 
     def lk_level_own(self, k: int) -> None:
         plan, s = self.plan, self.strips[k]
@@ -286,14 +346,14 @@ class StripRunner:
         self.ctx.lk_level_strip_device(self.prev[k], self.next[k], s.w, s.by0, s.h, s.y0 - s.by0, s.y1 - s.by0, plan.win,
                                        self.warp_mode, self.flow_scale, self.cum_in[k] if k < plan.levels - 1 else None,
                                        s.cy0, self.flow[k], cum_out=self.cum[k] if want_cum else None,
-                                       overflow_flag=self.overflow)
+                                       overflow_flag=self.overflow, stream=self.stream)
 
     def check_overflow(self) -> None:
         if int(self.overflow.item()) != 0:
             raise RuntimeError(f"rank {self.rank}: a warp sample reached past the exchanged halo rows: raise "
                                f"StripPlan.reach (currently {self.plan.reach} rows)")
 
-    def solve(self) -> None:
+    def solve(self, check: bool = True) -> None:
         """Coarse to fine: exchange cum_{k+1} halo rows, run the fused strip kernel on own rows."""
         plan = self.plan
         self.overflow.zero_()
@@ -301,7 +361,8 @@ class StripRunner:
             if k < plan.levels - 1:
                 self._run(self.cum_exchange(k))
             self.lk_level_own(k)
-        self.check_overflow()
+        if check:
+            self.check_overflow()
 
     def own_flow(self, k: int):
         s = self.strips[k]

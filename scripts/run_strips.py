@@ -11,13 +11,15 @@ import torch
 import torch.distributed as dist
 from bench import synth_pairs_torch
 from cuda_optical_flow_2_b200 import Context, WARP_BILINEAR
-from cuda_optical_flow_2_b200.dist import DistTransport, StripPlan, StripRunner
+from cuda_optical_flow_2_b200.dist import DistTransport, GatherTransport, StripPlan, StripRunner
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--w", type=int, default=7680); ap.add_argument("--h", type=int, default=4320)
 ap.add_argument("--levels", type=int, default=4); ap.add_argument("--win", type=int, default=9)
 ap.add_argument("--reps", type=int, default=10); ap.add_argument("--reach", type=int, default=16)
 ap.add_argument("--check", action="store_true")
+ap.add_argument("--transport", default="gather", choices=["gather", "p2p"], help="halo exchange: one all-gather per exchange (graph-capturable) or grouped send/recv")
+ap.add_argument("--graph", action="store_true", help="capture one pair in a CUDA graph and replay it (1 GPU: works, -8 %; with NCCL exchanges the capture hung on this stack, PyTorch 2.11 + NCCL 2.28: unresolved)")
 a = ap.parse_args()
 world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0")); local = int(os.environ.get("LOCAL_RANK", "0"))
 torch.cuda.set_device(local); dev = torch.device("cuda", local)
@@ -31,12 +33,35 @@ class Solo(DistTransport):
     def exchange(self, sends, recvs):
         if world > 1: super().exchange(sends, recvs)
 
-rn = StripRunner(ctx, plan, rank, Solo() if world > 1 else type("T", (), {"exchange": lambda self, s, r: None})(), dev, WARP_BILINEAR)
+if world == 1:
+    tp = type("T", (), {"exchange": lambda self, s, r: None})()
+elif a.transport == "gather":
+    tp = GatherTransport(rank, world, dev)
+else:
+    tp = Solo()
+rn = StripRunner(ctx, plan, rank, tp, dev, WARP_BILINEAR)
 s0 = rn.strips[0]
+pr, nr = prev[0, s0.y0:s0.y1, :a.w], nxt[0, s0.y0:s0.y1, :a.w]
 def one():
-    rn.load_level0(prev[0, s0.y0:s0.y1, :a.w], nxt[0, s0.y0:s0.y1, :a.w])
-    rn.build_pyramid(); rn.solve()
-for _ in range(3): one()
+    rn.step(pr, nr)
+side = torch.cuda.Stream(dev)
+side.wait_stream(torch.cuda.current_stream(dev))
+with torch.cuda.stream(side):
+    rn.use_current_stream()
+    for _ in range(3): one()
+    rn.check_overflow()
+    if a.graph:
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=side, capture_error_mode="thread_local"):  # the NCCL watchdog thread queries events
+            rn.use_current_stream()
+            one()
+        one = g.replay
+        for _ in range(2): one()
+torch.cuda.current_stream(dev).wait_stream(side)
+torch.cuda.synchronize()
+if not a.graph:
+    rn.stream = torch.cuda.current_stream(dev).cuda_stream
 def barrier():
     if world > 1: dist.barrier()
     torch.cuda.synchronize()
@@ -64,5 +89,5 @@ if rank == 0:
            sum((hi - lo) * (a.w >> (k + 1)) * 8 for k in range(a.levels) for _, lo, hi, _ in plan.cum_messages(k, 0))
     print(json.dumps({"mode": "row-strips", "w": a.w, "h": a.h, "levels": a.levels, "win": a.win, "n_gpus": world,
                       "ms_per_pair": t.item(), "mpx_pairs_per_s": a.w * a.h / 1e6 / (t.item() / 1e3),
-                      "bit_identical_to_whole_frame": ok, "halo_bytes_sent_rank0_per_pair": halo}), flush=True)
+                      "bit_identical_to_whole_frame": ok, "cuda_graph": bool(a.graph), "transport": a.transport if world > 1 else None, "halo_bytes_sent_rank0_per_pair": halo}), flush=True)
 if world > 1: dist.destroy_process_group()

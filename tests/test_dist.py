@@ -59,21 +59,22 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _gloo_worker(rank, world, port, q):
+def _gloo_worker(rank, world, port, q, transport="p2p"):
     """Each rank fills its own rows with a global-row pattern; after the exchange its buffer (own rows
     + halo) must equal the pattern of the whole image, for images and for the coarser flow."""
     sys.path.insert(0, ROOT)
     import torch
     import torch.distributed as dist
 
-    from cuda_optical_flow_2_b200.dist import DistTransport, StripPlan, StripRunner
+    from cuda_optical_flow_2_b200.dist import DistTransport, GatherTransport, StripPlan, StripRunner
 
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         W, H, levels, win = 96, 160, 3, 5
         plan = StripPlan(W, H, levels, win, world, reach=4)
-        rn = StripRunner(None, plan, rank, DistTransport(), torch.device("cpu"))
+        tp = GatherTransport(rank, world, torch.device("cpu")) if transport == "gather" else DistTransport()
+        rn = StripRunner(None, plan, rank, tp, torch.device("cpu"))
         ok = True
         for k in range(levels):
             s = rn.strips[k]
@@ -103,14 +104,15 @@ def _gloo_worker(rank, world, port, q):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world", [2, 3])
-def test_halo_exchange_over_gloo(world):
+@pytest.mark.parametrize("world,transport", [(2, "p2p"), (3, "p2p"), (2, "gather"), (3, "gather")])
+def test_halo_exchange_over_gloo(world, transport):
+    """Grouped send/recv, and the one-all-gather-per-exchange transport that CUDA graphs can capture."""
     import torch.multiprocessing as mp
 
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_gloo_worker, args=(r, world, port, q)) for r in range(world)]
+    procs = [ctx.Process(target=_gloo_worker, args=(r, world, port, q, transport)) for r in range(world)]
     for p in procs:
         p.start()
     results = [q.get(timeout=120) for _ in range(world)]
