@@ -137,6 +137,37 @@ def test_flow_pairs_device_identical_to_oracle(ctx, oracle, mode, w, h, levels, 
         assert_flow_identical(total[i].cpu().numpy(), cums[0], f"pair {i} total flow")
 
 
+@pytest.mark.parametrize("case", ["far_shift", "split_motion", "coarse_outliers"])
+def test_staged_window_and_fallbacks_identical_to_oracle(ctx, oracle, case):
+    """The warped levels gather from a window of `next` staged around the tile, displaced by the local coarser
+    flow.  far_shift: a global motion far larger than the window margin (the window follows it); split_motion:
+    two halves moving apart, so blocks near the seam leave the window and take the general path; coarse_outliers:
+    large flat areas whose unthresholded solve gives inf / NaN / huge flow on the coarser levels."""
+    torch = _torch()
+    from cuda_optical_flow_2_b200 import WARP_BILINEAR, planar_to_device
+
+    w, h, levels, win = 640, 480, 3, 9
+    prev = oracle.make_frame(w, h, 0, 0, 8, 4242)
+    if case == "far_shift":
+        nxt = oracle.make_frame(w, h, 41.5, -27.25, 8, 4242)
+    elif case == "split_motion":
+        a, b = oracle.make_frame(w, h, 13.0, 9.5, 8, 4242), oracle.make_frame(w, h, -14.5, -11.0, 8, 4242)
+        nxt = np.where(np.arange(w)[None, :] < w // 2, a, b).astype(np.uint8)
+    else:
+        prev = prev.copy()
+        prev[100:300, 50:400] = 128  # flat: det == 0 there
+        prev[350:, 500:] = 0
+        nxt = np.roll(prev, (2, 3), axis=(0, 1))
+    total = torch.empty((1, h, w, 2), dtype=torch.float32, device="cuda")
+    flows = ctx.flow_pairs_device(planar_to_device(prev[None]), planar_to_device(nxt[None]), w, levels, win,
+                                  warp_mode=WARP_BILINEAR, total_flow=total)
+    torch.cuda.synchronize()
+    ref, cums = oracle.flow_pair(prev, nxt, levels, win, oracle.WARP_BILINEAR, oracle.SUMS_EXACT, 1.0, want_cum=True)
+    for k in range(levels - 1, -1, -1):
+        assert_flow_identical(flows[k][0].cpu().numpy(), ref[k], f"{case} level {k}")
+    assert_flow_identical(total[0].cpu().numpy(), cums[0], f"{case} total flow")
+
+
 def test_flow_scale(ctx, oracle):
     torch = _torch()
     from cuda_optical_flow_2_b200 import planar_to_device
