@@ -72,6 +72,8 @@ SIGNATURES = {
     "ofb_stream_create": (C.c_int, [_vp, C.POINTER(OfbParams), C.c_int, C.c_double, C.c_double, C.POINTER(_vp)]),
     "ofb_stream_push_bgr_host": (C.c_int, [_vp, u8p, C.POINTER(f32p), f32p, i32p]),
     "ofb_stream_destroy": (C.c_int, [_vp]),
+    "ofb_conv_3ch_1ch_u8_u8_host": (C.c_int, [_vp, u8p, C.c_int, C.c_int, u8p, f32p, C.c_int, C.c_int]),
+    "ofb_debug_view_host_u8c3": (C.c_int, [_vp, u8p, u8p, C.c_int, C.c_int, C.c_int, C.c_int, u8p]),
     "ofb_compose_flow_host": (C.c_int, [_vp, C.POINTER(f32p), C.c_int, C.c_int, C.c_int, C.c_int, f32p]),
     "ofb_flow_arrows_host": (C.c_int, [_vp, C.POINTER(f32p), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, i32p, C.c_int, i32p]),
     "ofb_write_flo": (C.c_int, [C.c_char_p, f32p, C.c_int, C.c_int]),

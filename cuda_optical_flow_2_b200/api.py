@@ -153,6 +153,23 @@ class Context:
         ptrs = (L.f32p * (level + 1))(*[a.ctypes.data_as(L.f32p) for a in arrs])
         L.check(self._lib.ofb_inverse_matrix_f32_host(self._h, *[s.ctypes.data_as(L.f32p) for s in sums], ptrs, level, w, h))
 
+    # ---- debug derivative views: showTest (main.cu:19-92) without the windows ----
+    def conv_3ch_1ch_tiled(self, src: np.ndarray, w: int, h: int, mask: np.ndarray, mw: int, mh: int) -> np.ndarray:
+        """gpu::conv_3ch_1ch_tiled: (h, w, 3) u8 in, (h, w) u8 out."""
+        mask = np.ascontiguousarray(mask, np.float32).reshape(-1)
+        dst = np.empty((h, w), np.uint8)
+        L.check(self._lib.ofb_conv_3ch_1ch_u8_u8_host(self._h, _u8(src).ctypes.data_as(L.u8p), w, h, dst.ctypes.data_as(L.u8p),
+                                                      mask.ctypes.data_as(L.f32p), mw, mh))
+        return dst
+
+    def debug_view(self, prev_level: Optional[np.ndarray], cur_level: np.ndarray, w: int, h: int, level: int, which: int) -> np.ndarray:
+        """One window of showTest: thresholded derivative of a pyramid level, upscaled by 2^level."""
+        out = np.empty((h << level, w << level), np.uint8)
+        pp = _u8(prev_level).ctypes.data_as(L.u8p) if prev_level is not None else None
+        L.check(self._lib.ofb_debug_view_host_u8c3(self._h, pp, _u8(cur_level).ctypes.data_as(L.u8p), w, h, level, which,
+                                                   out.ctypes.data_as(L.u8p)))
+        return out
+
     # ---- flow composition and export: the headless part of visualizeFlowField (main.cu:114-174) ----
     def compose_flow(self, flow_pyramid: Sequence[np.ndarray], w: int, h: int, levels: int, level: int = 0) -> np.ndarray:
         """Total flow of `level` from the residual pyramid (composition rule main.cu:136-147)."""

@@ -919,6 +919,55 @@ int ofb_bilateral_planar_device(ofb_ctx *c, const uint8_t *gray_d, size_t pitch,
                             static_cast<cudaStream_t>(stream), &c->launches);
 }
 
+// ---- debug derivative views (main.cu:19-92) -----------------------------------------------------
+
+int ofb_conv_3ch_1ch_u8_u8_host(ofb_ctx *c, const unsigned char *src_h, int w, int h, unsigned char *dest_h, const float *mask,
+                                int mw, int mh)
+{
+    OFB_CHECK_CTX(c);
+    if (!src_h || !dest_h || !mask || w < 1 || h < 1) {
+        set_error("conv (u8): bad arguments");
+        return OFB_ERR_INVALID;
+    }
+    OFB_GUARD(c);
+    const size_t n = (size_t)w * h;
+    Carver cv;
+    const size_t os = cv.take(n * 3), od = cv.take(n);
+    int rc = ws_reserve(c, cv.off);
+    if (rc) return rc;
+    cudaStream_t st = c->stream;
+    OFB_CUDA_TRY(cudaMemcpyAsync(c->ws + os, src_h, n * 3, cudaMemcpyHostToDevice, st));
+    rc = launch_conv_c3_u8(c->ws + os, w, h, c->ws + od, mask, mw, mh, st, &c->launches);
+    if (rc) return rc;
+    OFB_CUDA_TRY(cudaMemcpyAsync(dest_h, c->ws + od, n, cudaMemcpyDeviceToHost, st));
+    OFB_CUDA_TRY(cudaStreamSynchronize(st));
+    return OFB_OK;
+}
+
+int ofb_debug_view_host_u8c3(ofb_ctx *c, const unsigned char *prev_level_h, const unsigned char *cur_level_h, int w, int h,
+                             int level, int which, unsigned char *out_h)
+{
+    OFB_CHECK_CTX(c);
+    if (!cur_level_h || !out_h || (which == OFB_VIEW_T && !prev_level_h) || w < 1 || h < 1 || level < 0 || level > 12) {
+        set_error("debug_view: bad arguments");
+        return OFB_ERR_INVALID;
+    }
+    OFB_GUARD(c);
+    const size_t n = (size_t)w * h, no = ((size_t)w << level) * ((size_t)h << level);
+    Carver cv;
+    const size_t oc = cv.take(n * 3), op = cv.take(n * 3), oo = cv.take(no);
+    int rc = ws_reserve(c, cv.off);
+    if (rc) return rc;
+    cudaStream_t st = c->stream;
+    OFB_CUDA_TRY(cudaMemcpyAsync(c->ws + oc, cur_level_h, n * 3, cudaMemcpyHostToDevice, st));
+    if (which == OFB_VIEW_T) OFB_CUDA_TRY(cudaMemcpyAsync(c->ws + op, prev_level_h, n * 3, cudaMemcpyHostToDevice, st));
+    rc = launch_debug_view(c->ws + op, c->ws + oc, w, h, level, which, c->ws + oo, st, &c->launches);
+    if (rc) return rc;
+    OFB_CUDA_TRY(cudaMemcpyAsync(out_h, c->ws + oo, no, cudaMemcpyDeviceToHost, st));
+    OFB_CUDA_TRY(cudaStreamSynchronize(st));
+    return OFB_OK;
+}
+
 // ---- flow composition and export (the headless part of main.cu:114-174) ----------------------
 
 int ofb_compose_flow_host(ofb_ctx *c, float *const *flow_pyramid_h, int w, int h, int levels, int level, float *total_h)

@@ -61,6 +61,10 @@ int launch_c3_to_planar(const uint8_t *src_c3, int w, int h, int n_images, uint8
                         size_t dst_stride, cudaStream_t stream, unsigned long long *launches);
 int launch_conv_c3_f32(const uint8_t *src_c3, int w, int h, float *dst, const float *mask_host, int mw, int mh,
                        cudaStream_t stream, unsigned long long *launches);
+int launch_conv_c3_u8(const uint8_t *src_c3, int w, int h, uint8_t *dst, const float *mask_host, int mw, int mh,
+                      cudaStream_t stream, unsigned long long *launches);
+int launch_debug_view(const uint8_t *prev_c3, const uint8_t *cur_c3, int w, int h, int k, int which, uint8_t *out,
+                      cudaStream_t stream, unsigned long long *launches);
 int launch_srm_f32(const float *a, const float *b, int w, int h, int ww, int wh, float *dst, cudaStream_t stream,
                    unsigned long long *launches);
 int launch_inverse_f32(const float *sxx, const float *syy, const float *sxy, const float *sxt, const float *syt,

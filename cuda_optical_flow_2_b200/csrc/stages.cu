@@ -52,6 +52,89 @@ int launch_conv_c3_f32(const uint8_t *src_c3, int w, int h, float *dst, const fl
     return OFB_OK;
 }
 
+// g_conv_3ch_1ch_constant, OptFlowGpu.cu:380-423 (what gpu::conv_3ch_1ch_tiled launches, :741-766): the u8 result
+// variant used by the debug views.  An INT accumulator: `tmp += src * mask` per tap in row-major order is int ->
+// float, one fused multiply-add (FFMA in the reference TU's SASS), truncation back to int, every tap; out-of-image
+// taps and zero mask entries are skipped; the result is cast to unsigned char (wraps).
+__device__ __forceinline__ int conv_u8_at(const uint8_t *__restrict__ src_c3, int w, int h, const Mask25 &mask, int mw, int mh,
+                                          int x, int y)
+{
+    const int hmw = mw >> 1, hmh = mh >> 1;
+    int tmp = 0;
+    for (int i = 0; i < mh; i++) {
+        const int ty = y - hmh + i;
+        if (ty < 0 || ty >= h) continue;
+        for (int j = 0; j < mw; j++) {
+            const int tx = x - hmw + j;
+            if (tx < 0 || tx >= w) continue;
+            const float m = mask.m[i * mw + j];
+            if (m == 0.0f) continue;
+            tmp = __float2int_rz(__fmaf_rn((float)__ldg(src_c3 + ((size_t)ty * w + tx) * 3), m, (float)tmp));
+        }
+    }
+    return tmp;
+}
+
+__global__ void __launch_bounds__(256)
+conv_c3_u8_kernel(const uint8_t *__restrict__ src_c3, int w, int h, uint8_t *__restrict__ dst, const Mask25 mask, int mw, int mh)
+{
+    const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
+    if (x >= w || y >= h) return;
+    dst[(size_t)y * w + x] = (uint8_t)conv_u8_at(src_c3, w, h, mask, mw, mh, x, y);
+}
+
+int launch_conv_c3_u8(const uint8_t *src_c3, int w, int h, uint8_t *dst, const float *mask_host, int mw, int mh,
+                      cudaStream_t stream, unsigned long long *launches)
+{
+    if (w < 1 || h < 1 || mw < 1 || mh < 1 || mw * mh > 25) {
+        set_error("conv: bad geometry (w %d h %d mask %dx%d, at most 25 taps)", w, h, mw, mh);
+        return OFB_ERR_INVALID;
+    }
+    Mask25 mk;
+    for (int i = 0; i < 25; i++) mk.m[i] = (i < mw * mh) ? mask_host[i] : 0.0f;
+    dim3 block(32, 8), grid((unsigned)((w + 31) / 32), (unsigned)((h + 7) / 8));
+    conv_c3_u8_kernel<<<grid, block, 0, stream>>>(src_c3, w, h, dst, mk, mw, mh);
+    OFB_CUDA_TRY(cudaGetLastError());
+    if (launches) ++*launches;
+    return OFB_OK;
+}
+
+// One window of showTest (main.cu:19-92) for a pyramid level of size w x h, written at full resolution
+// (w << k) x (h << k): the u8 convolution above with Dx_3x3 / Dy_3x3 on cur, or with Dt_3x3_n on cur minus on prev
+// (cpu::sub_arr, unsigned char wrap-around), then utils::cleanup_outliers (>= 240 or < 20 -> 0, else 255) and
+// utils::upscale_1ch (nearest).  One thread per OUTPUT pixel (coalesced stores; the 3x3 taps are cache hits).
+__global__ void __launch_bounds__(256)
+debug_view_kernel(const uint8_t *__restrict__ prev_c3, const uint8_t *__restrict__ cur_c3, int w, int h, int k, int which,
+                  const Mask25 mask, uint8_t *__restrict__ out)
+{
+    const int ox = blockIdx.x * 32 + threadIdx.x, oy = blockIdx.y * 8 + threadIdx.y;
+    if (ox >= (w << k) || oy >= (h << k)) return;
+    const int x = ox >> k, y = oy >> k;
+    uint8_t v = (uint8_t)conv_u8_at(cur_c3, w, h, mask, 3, 3, x, y);
+    if (which == 2) v = (uint8_t)(v - (uint8_t)conv_u8_at(prev_c3, w, h, mask, 3, 3, x, y));
+    out[(size_t)oy * ((size_t)w << k) + ox] = (v >= 240 || v < 20) ? 0 : 255;
+}
+
+int launch_debug_view(const uint8_t *prev_c3, const uint8_t *cur_c3, int w, int h, int k, int which, uint8_t *out,
+                      cudaStream_t stream, unsigned long long *launches)
+{
+    static const float DX[9] = {-1, 0, 1, -2, 0, 2, -1, 0, 1};                                                 // kernels.cpp:6-10
+    static const float DY[9] = {-1, -2, -1, 0, 0, 0, 1, 2, 1};                                                 // kernels.cpp:15-19
+    static const float DTN[9] = {0.0666f, 0.1333f, 0.0666f, 0.1333f, 0.2f, 0.1333f, 0.0666f, 0.1333f, 0.0666f}; // kernels.cpp:25-28
+    if (w < 1 || h < 1 || k < 0 || k > 12 || which < 0 || which > 2 || ((size_t)h << k) > 0x7fffffffull / ((size_t)w << k)) {
+        set_error("debug_view: bad arguments (w %d h %d level %d view %d)", w, h, k, which);
+        return OFB_ERR_INVALID;
+    }
+    const float *m = which == 0 ? DX : which == 1 ? DY : DTN;
+    Mask25 mk;
+    for (int i = 0; i < 25; i++) mk.m[i] = i < 9 ? m[i] : 0.0f;
+    dim3 block(32, 8), grid((unsigned)(((w << k) + 31) / 32), (unsigned)(((h << k) + 7) / 8));
+    debug_view_kernel<<<grid, block, 0, stream>>>(prev_c3, cur_c3, w, h, k, which, mk, out);
+    OFB_CUDA_TRY(cudaGetLastError());
+    if (launches) ++*launches;
+    return OFB_OK;
+}
+
 // g_srm_1ch_float, OptFlowGpu.cu:1549-1588: windowed sum of a*b, out-of-image taps skipped,
 // `tmp += a*b` (one fma per tap) in row-major tap order.  A 32x8 output tile stages its
 // (32+ww-1) x (8+wh-1) footprint of both inputs in shared memory; out-of-image positions are

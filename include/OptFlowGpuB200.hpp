@@ -94,6 +94,15 @@ inline void conv_3ch_1ch_tiled_uchar_float(const unsigned char *src_h, int w, in
     report("conv_3ch_1ch_tiled_uchar_float", ofb_conv_3ch_1ch_u8_f32_host(c, src_h, w, h, dest_h, mask_t, mw, mh));
 }
 
+// gpu::conv_3ch_1ch_tiled (OptFlowGpu.cu:741-766), the u8 result variant the debug views of main.cu:19-92 use.
+inline void conv_3ch_1ch_tiled(const unsigned char *src_h, int w, int h, unsigned char *dest_h, const float *mask_t, int mw,
+                               int mh)
+{
+    ofb_ctx *c = default_context();
+    if (!c) return;
+    report("conv_3ch_1ch_tiled", ofb_conv_3ch_1ch_u8_u8_host(c, src_h, w, h, dest_h, mask_t, mw, mh));
+}
+
 // OptFlowGpu.cuh:25.
 inline void srm_1ch_float(const float *arr1_h, const float *arr2_h, int w, int h, int ww, int wh, float *dest_h)
 {

@@ -193,6 +193,22 @@ int ofb_stream_push_bgr_host(ofb_stream *s, const unsigned char *frame_bgr, floa
                              float *total_flow_h, int *has_flow);
 int ofb_stream_destroy(ofb_stream *s);
 
+/* ---- debug derivative views: showTest (main.cu:19-92) without the windows ------------------------------------------
+ * ofb_conv_3ch_1ch_u8_u8_host replaces gpu::conv_3ch_1ch_tiled (OptFlowGpu.cuh; OptFlowGpu.cu:741-766, kernel
+ *   :380-423): 3-channel u8 in (channel 0 is read), u8 out; an int accumulator truncated after every tap, result
+ *   cast to unsigned char.
+ * ofb_debug_view_host_u8c3: one window of showTest for pyramid level `level` (images of size w x h, 3-channel):
+ *   OFB_VIEW_X: Dx_3x3 on cur (main.cu:44-56), OFB_VIEW_Y: Dy_3x3 on cur (:76-88), OFB_VIEW_T: Dt_3x3_n on cur minus
+ *   on prev with unsigned char wrap-around (:57-75); then utils::cleanup_outliers and utils::upscale_1ch by
+ *   2^level.  out_h: (w << level) * (h << level) bytes, values 0 / 255.  prev_level_h may be NULL for X and Y. */
+#define OFB_VIEW_X 0
+#define OFB_VIEW_Y 1
+#define OFB_VIEW_T 2
+int ofb_conv_3ch_1ch_u8_u8_host(ofb_ctx *ctx, const unsigned char *src_h, int w, int h, unsigned char *dest_h,
+                                const float *mask, int mw, int mh);
+int ofb_debug_view_host_u8c3(ofb_ctx *ctx, const unsigned char *prev_level_h, const unsigned char *cur_level_h, int w, int h,
+                             int level, int which, unsigned char *out_h);
+
 /* ---- flow composition and export: the headless part of visualizeFlowField (main.cu:114-174) --------------------
  * flow_pyramid_h[k]: residual flow of level k, (h>>k)*(w>>k)*2 floats, as gpu::calc_opt_flow leaves it
  * (main.cu:95-104, 256-262); only levels level..levels-1 are read.

@@ -521,3 +521,68 @@ void orc_make_frame(uint8_t *img, int w, int h, float dx, float dy, int cell, ui
         }
     free(g);
 }
+
+
+/* ---- debug derivative views, main.cu:19-92 ------------------------------------------------
+ * orc_conv_u8: gpu::conv_3ch_1ch_tiled, which launches g_conv_3ch_1ch_constant (OptFlowGpu.cu:741-766 ->
+ * :380-423): per pixel an INT accumulator, `tmp += src[ch0] * mask` per tap in row-major order -- i.e. int ->
+ * float, one fused multiply-add (nvcc contracts it: FFMA in the reference TU's sm_100a SASS), truncation back to
+ * int, every tap -- out-of-image taps and zero mask entries skipped, result cast to unsigned char (wraps).
+ * src: planar u8 (channel 0 of the reference's 3-channel image). */
+void orc_conv_u8(const uint8_t *src, int w, int h, const float *mask, int mw, int mh, uint8_t *dst)
+{
+    const int hmw = mw >> 1, hmh = mh >> 1;
+    for (int y = 0; y < h; y++)
+        for (int x = 0; x < w; x++) {
+            int tmp = 0;
+            for (int i = 0; i < mh; i++) {
+                const int ty = y - hmh + i;
+                if (ty < 0 || ty >= h) continue;
+                for (int j = 0; j < mw; j++) {
+                    const int tx = x - hmw + j;
+                    if (tx < 0 || tx >= w) continue;
+                    const float m = mask[i * mw + j];
+                    if (m == 0.0f) continue;
+                    tmp = (int)fmaf((float)src[(size_t)ty * w + tx], m, (float)tmp);
+                }
+            }
+            dst[(size_t)y * w + x] = (uint8_t)tmp;
+        }
+}
+
+/* orc_debug_view: one window of showTest (main.cu:19-92) for pyramid level k of size w x h.
+ * which 0: Dx_3x3 on cur (:44-56); 1: Dy_3x3 on cur (:76-88); 2: Dt_3x3_n on cur minus on prev with unsigned
+ * char wrap-around (cpu::sub_arr, OptFlowCPU.cpp:11-17; :57-75).  Then utils::cleanup_outliers
+ * (OptFlowUtils.cpp:5-20: >= 240 or < 20 -> 0, else 255) and utils::upscale_1ch by 2^k (:44-61, nearest).
+ * out: (w << k) x (h << k). */
+static const float ORC_DTN[9] = {0.0666f, 0.1333f, 0.0666f, 0.1333f, 0.2f, 0.1333f, 0.0666f, 0.1333f, 0.0666f}; /* :25-28 */
+int orc_debug_view(const uint8_t *prev, const uint8_t *cur, int w, int h, int k, int which, uint8_t *out)
+{
+    if (w < 1 || h < 1 || k < 0 || k > 12 || which < 0 || which > 2) return 1;
+    const size_t n = (size_t)w * h;
+    uint8_t *a = (uint8_t *)malloc(n), *b = (uint8_t *)malloc(n);
+    if (!a || !b) {
+        free(a);
+        free(b);
+        return 2;
+    }
+    if (which == 2) {
+        orc_conv_u8(cur, w, h, ORC_DTN, 3, 3, a);
+        orc_conv_u8(prev, w, h, ORC_DTN, 3, 3, b);
+        for (size_t i = 0; i < n; i++) a[i] = (uint8_t)(a[i] - b[i]);
+    } else {
+        orc_conv_u8(cur, w, h, which == 0 ? ORC_DX : ORC_DY, 3, 3, a);
+    }
+    const int s = 1 << k;
+    const size_t ow = (size_t)w << k;
+    for (int y = 0; y < h; y++)
+        for (int x = 0; x < w; x++) {
+            const uint8_t v = a[(size_t)y * w + x];
+            const uint8_t c = (v >= 240 || v < 20) ? 0 : 255;
+            for (int p = 0; p < s; p++)
+                for (int q = 0; q < s; q++) out[((size_t)y * s + p) * ow + (size_t)x * s + q] = c;
+        }
+    free(a);
+    free(b);
+    return 0;
+}

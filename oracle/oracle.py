@@ -368,3 +368,76 @@ def read_flo(path: str) -> np.ndarray:
         w, h = np.frombuffer(f.read(8), np.int32)
         assert tag == np.float32(202021.25)
         return np.frombuffer(f.read(), np.float32).reshape(h, w, 2).copy()
+
+
+# ---- debug derivative views (main.cu:19-92) ------------------------------------------------------
+VIEW_X, VIEW_Y, VIEW_T = 0, 1, 2
+
+
+def conv_u8(src: np.ndarray, mask: np.ndarray) -> np.ndarray:
+    """gpu::conv_3ch_1ch_tiled (OptFlowGpu.cu:741-766): u8 planar in, u8 out, int accumulator truncated every tap."""
+    h, w = src.shape
+    src = np.ascontiguousarray(src, np.uint8)
+    mask = np.ascontiguousarray(mask, np.float32)
+    dst = np.empty((h, w), np.uint8)
+    lib().orc_conv_u8(_p(src, _u8p), w, h, _p(mask, _f32p), mask.shape[1], mask.shape[0], _p(dst, _u8p))
+    return dst
+
+
+def debug_view(prev: np.ndarray, cur: np.ndarray, k: int, which: int) -> np.ndarray:
+    """One window of showTest for level k images (planar u8): thresholded derivative, upscaled by 2^k."""
+    h, w = cur.shape
+    prev = np.ascontiguousarray(prev, np.uint8)
+    cur = np.ascontiguousarray(cur, np.uint8)
+    out = np.empty((h << k, w << k), np.uint8)
+    rc = lib().orc_debug_view(_p(prev, _u8p), _p(cur, _u8p), w, h, k, which, _p(out, _u8p))
+    if rc != 0:
+        raise ValueError("orc_debug_view: bad arguments")
+    return out
+
+
+def _c3(img: np.ndarray) -> np.ndarray:
+    return np.ascontiguousarray(np.repeat(img[:, :, None], 3, axis=2))
+
+
+def ref_mask_dt_n() -> np.ndarray:
+    r = ref()
+    r.ref_mask_dt_n.restype = C.POINTER(C.c_float)
+    return np.ctypeslib.as_array(r.ref_mask_dt_n(), shape=(9,)).reshape(3, 3).copy()
+
+
+def ref_cpu_conv_u8(img: np.ndarray, mask: np.ndarray) -> np.ndarray:
+    """cpu::conv_3ch_to_1ch (OptFlowCPU.cpp:75-110), the host twin of the u8 convolution (no fused multiply-add)."""
+    h, w = img.shape
+    src, mask = _c3(img), np.ascontiguousarray(mask, np.float32)
+    dst = np.empty((h, w), np.uint8)
+    ref().ref_cpu_conv_3ch_to_1ch(_p(src, _u8p), w, h, _p(dst, _u8p), _p(mask, _f32p), mask.shape[1], mask.shape[0])
+    return dst
+
+
+def ref_gpu_conv_u8(img: np.ndarray, mask: np.ndarray) -> np.ndarray:
+    """gpu::conv_3ch_1ch_tiled itself (needs a GPU)."""
+    h, w = img.shape
+    src, mask = _c3(img), np.ascontiguousarray(mask, np.float32)
+    dst = np.empty((h, w), np.uint8)
+    ref().ref_gpu_conv_3ch_1ch_tiled(_p(src, _u8p), w, h, _p(dst, _u8p), _p(mask, _f32p), mask.shape[1], mask.shape[0])
+    return dst
+
+
+def ref_debug_view(prev: np.ndarray, cur: np.ndarray, k: int, which: int, conv=None) -> np.ndarray:
+    """showTest composed from the reference's own functions: conv (GPU by default), cpu::sub_arr,
+    utils::cleanup_outliers, utils::upscale_1ch."""
+    conv = conv or ref_gpu_conv_u8
+    h, w = cur.shape
+    masks = {VIEW_X: np.array([[-1, 0, 1], [-2, 0, 2], [-1, 0, 1]], np.float32),
+             VIEW_Y: np.array([[-1, -2, -1], [0, 0, 0], [1, 2, 1]], np.float32), VIEW_T: ref_mask_dt_n()}
+    a = conv(cur, masks[which])
+    if which == VIEW_T:
+        b = conv(prev, masks[which])
+        ref().ref_cpu_sub_arr(_p(a, _u8p), _p(b, _u8p), w * h, _p(b, _u8p))  # main.cu:65: dest = second operand
+        a = b
+    a = np.ascontiguousarray(a)
+    ref().ref_utils_cleanup_outliers(_p(a, _u8p), w, h)
+    out = np.empty((h << k, w << k), np.uint8)
+    ref().ref_utils_upscale_1ch(_p(a, _u8p), w, h, k, _p(out, _u8p))
+    return out

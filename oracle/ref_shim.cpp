@@ -90,6 +90,20 @@ void ref_gpu_bilinear_filter(unsigned char *src, unsigned char *gray, unsigned c
 
 // ---- GPU-side functions of the reference (need a GPU; launch-valid only when w,h are multiples
 // of 32 and (w/32)*(h/32) <= 1024) ----
+// the debug derivative views (main.cu:19-92)
+const float *ref_mask_dt_n() { return Dt_3x3_n; }
+void ref_gpu_conv_3ch_1ch_tiled(const unsigned char *src, int w, int h, unsigned char *dest, const float *mask, int mw, int mh)
+{
+    gpu::conv_3ch_1ch_tiled(src, w, h, dest, mask, mw, mh);
+}
+void ref_cpu_conv_3ch_to_1ch(const unsigned char *src, int w, int h, unsigned char *dest, const float *mask, int mw, int mh)
+{
+    cpu::conv_3ch_to_1ch(src, w, h, dest, mask, mw, mh);
+}
+void ref_cpu_sub_arr(unsigned char *a, unsigned char *b, int n, unsigned char *dest) { cpu::sub_arr(a, b, n, dest); }
+void ref_utils_cleanup_outliers(unsigned char *src, int w, int h) { utils::cleanup_outliers(src, w, h); }
+void ref_utils_upscale_1ch(unsigned char *src, int w, int h, int n, unsigned char *dest) { utils::upscale_1ch(src, w, h, n, dest); }
+
 void ref_gpu_gauss_pyramid(unsigned char **pyramid, int w, int h, int levels)
 {
     gpu::gauss_pyramid(pyramid, w, h, levels, GAUS_KERNEL_3x3, 3, 3); // main.cu:250
