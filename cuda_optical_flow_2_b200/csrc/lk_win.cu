@@ -30,14 +30,14 @@ static int launch_one(const LkLevelArgs &a, cudaStream_t stream, unsigned long l
     CUtensorMap tmP, tmQ;
     int rc = lk_make_image_map(&tmP, a.prev, a.w, a.h_local, a.n_pairs, a.pitch, a.image_stride, LK_TILE_W, C::CH);
     if (rc) return rc;
-    // next: the same box as prev on the coarsest level, the window with margin on bilinearly warped levels
-    rc = lk_make_image_map(&tmQ, a.next, a.w, a.h_local, a.n_pairs, a.pitch, a.image_stride, MODE == 2 ? LK_NTW : LK_TILE_W,
-                           MODE == 2 ? C::NTH : C::CH);
+    // next: the same box as prev on the coarsest level, the window with margin on warped levels
+    rc = lk_make_image_map(&tmQ, a.next, a.w, a.h_local, a.n_pairs, a.pitch, a.image_stride, MODE != 0 ? LK_NTW : LK_TILE_W,
+                           MODE != 0 ? C::NTH : C::CH);
     if (rc) return rc;
     // coarser cumulative flow of bilinearly warped levels: tiles of NBR x LK_CTW vectors
     CUtensorMap tmC = tmP;
     int cum_tma = 0;
-    if (MODE == 2) {
+    if (MODE != 0) {
         rc = lk_make_flow_map(&tmC, a.cum_in, a.cum_w, a.cum_h_local, a.n_pairs, a.cum_pair_stride, LK_CTW, C::NBR, &cum_tma);
         if (rc) return rc;
     }
