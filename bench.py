@@ -386,7 +386,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--pairs", type=int, default=256, help="frame pairs per GPU per step (device-resident)")
-    ap.add_argument("--e2e-pairs", type=int, default=8, help="frame pairs per GPU per end-to-end step")
+    ap.add_argument("--e2e-pairs", type=int, default=32, help="frame pairs per GPU per end-to-end step")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

@@ -72,6 +72,14 @@ SIGNATURES = {
     "ofb_stream_create": (C.c_int, [_vp, C.POINTER(OfbParams), C.c_int, C.c_double, C.c_double, C.POINTER(_vp)]),
     "ofb_stream_push_bgr_host": (C.c_int, [_vp, u8p, C.POINTER(f32p), f32p, i32p]),
     "ofb_stream_destroy": (C.c_int, [_vp]),
+    "ofb_strips_nccl_unique_id": (C.c_int, [_vp]),
+    "ofb_strips_create": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, C.c_int, C.c_int,
+                                    _vp, C.POINTER(_vp)]),
+    "ofb_strips_own_rows": (C.c_int, [_vp, C.c_int, i32p, i32p]),
+    "ofb_strips_run_device": (C.c_int, [_vp, _vp, _vp, _sz, _vp]),
+    "ofb_strips_result": (C.c_int, [_vp, C.c_int, C.POINTER(_vp), C.POINTER(_vp)]),
+    "ofb_strips_check": (C.c_int, [_vp, _vp, i32p]),
+    "ofb_strips_destroy": (C.c_int, [_vp]),
     "ofb_conv_3ch_1ch_u8_u8_host": (C.c_int, [_vp, u8p, C.c_int, C.c_int, u8p, f32p, C.c_int, C.c_int]),
     "ofb_debug_view_host_u8c3": (C.c_int, [_vp, u8p, u8p, C.c_int, C.c_int, C.c_int, C.c_int, u8p]),
     "ofb_compose_flow_host": (C.c_int, [_vp, C.POINTER(f32p), C.c_int, C.c_int, C.c_int, C.c_int, f32p]),

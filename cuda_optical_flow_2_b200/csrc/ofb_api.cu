@@ -49,6 +49,11 @@ struct ofb_ctx {
 
 namespace ofb {
 
+// accessors for the other translation units (strips.cu): ofb_ctx stays private to this file
+int ctx_device(const ofb_ctx *c) { return c->device; }
+int ctx_sm_count(const ofb_ctx *c) { return c->sm_count; }
+unsigned long long *ctx_launch_counter(ofb_ctx *c) { return &c->launches; }
+
 struct DeviceGuard {
     int prev = -1;
     bool ok = false;

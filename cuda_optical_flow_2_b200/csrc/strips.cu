@@ -1,0 +1,415 @@
+// strips.cu -- row-strip solve of ONE large pair over several GPUs (BASELINE configs[4]), native host side.
+//
+// One process per GPU.  The strip schedule is the one of cuda_optical_flow_2_b200/dist.py (StripPlan: bounds fixed
+// on the coarsest level and doubled per finer level, image halo = window radius + stencil + warp reach, coarser
+// cumulative-flow halo), but here the whole pair -- own-row upload, per-level halo exchange, pyramid, fused level
+// kernels -- is enqueued on one CUDA stream from C++ with no host synchronisation, and the halo rows move by NCCL
+// send/recv (NVLink / NVSwitch) straight between the ranks' image and flow buffers: rows are contiguous, so there
+// is no staging copy.  The Python StripRunner does the same through torch and is exchange-latency bound (seven
+// exchanges per pair at ~100 us of host work each); this path costs a few microseconds of host work per operation.
+//
+// NCCL is not a link-time dependency of the library: libnccl.so.2 is opened on first use (inside a torch process
+// that is the copy torch already loaded), and every symbol is resolved with dlsym.
+#include "ofb_common.cuh"
+
+#include <dlfcn.h>
+
+#include <algorithm>
+#include <cstring>
+#include <mutex>
+#include <vector>
+
+struct ofb_ctx; // ofb_api.cu
+namespace ofb {
+// accessors implemented in ofb_api.cu (ofb_ctx is private to it)
+int ctx_device(const ofb_ctx *c);
+int ctx_sm_count(const ofb_ctx *c);
+unsigned long long *ctx_launch_counter(ofb_ctx *c);
+
+// ---- NCCL through dlopen ------------------------------------------------------------------------------------
+typedef struct ncclComm *ncclComm_t;
+struct NcclUniqueId {
+    char internal[128];
+};
+enum { NCCL_SUCCESS = 0, NCCL_UINT8 = 1 };
+struct NcclApi {
+    int (*GetUniqueId)(NcclUniqueId *);
+    int (*CommInitRank)(ncclComm_t *, int, NcclUniqueId, int);
+    int (*CommDestroy)(ncclComm_t);
+    int (*Send)(const void *, size_t, int, int, ncclComm_t, cudaStream_t);
+    int (*Recv)(void *, size_t, int, int, ncclComm_t, cudaStream_t);
+    int (*GroupStart)();
+    int (*GroupEnd)();
+    const char *(*GetErrorString)(int);
+    bool ok = false;
+};
+static NcclApi *nccl()
+{
+    static NcclApi api;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+        if (!h) return;
+        bool all = true;
+        auto sym = [&](const char *n) {
+            void *p = dlsym(h, n);
+            if (!p) all = false;
+            return p;
+        };
+        api.GetUniqueId = reinterpret_cast<decltype(api.GetUniqueId)>(sym("ncclGetUniqueId"));
+        api.CommInitRank = reinterpret_cast<decltype(api.CommInitRank)>(sym("ncclCommInitRank"));
+        api.CommDestroy = reinterpret_cast<decltype(api.CommDestroy)>(sym("ncclCommDestroy"));
+        api.Send = reinterpret_cast<decltype(api.Send)>(sym("ncclSend"));
+        api.Recv = reinterpret_cast<decltype(api.Recv)>(sym("ncclRecv"));
+        api.GroupStart = reinterpret_cast<decltype(api.GroupStart)>(sym("ncclGroupStart"));
+        api.GroupEnd = reinterpret_cast<decltype(api.GroupEnd)>(sym("ncclGroupEnd"));
+        api.GetErrorString = reinterpret_cast<decltype(api.GetErrorString)>(sym("ncclGetErrorString"));
+        api.ok = all;
+    });
+    return api.ok ? &api : nullptr;
+}
+#define OFB_NCCL_TRY(expr)                                                                                    \
+    do {                                                                                                      \
+        int _r = (expr);                                                                                      \
+        if (_r != NCCL_SUCCESS) {                                                                             \
+            ofb::set_error("%s:%d: %s failed: %s", __FILE__, __LINE__, #expr, ofb::nccl()->GetErrorString(_r)); \
+            return OFB_ERR_CUDA;                                                                              \
+        }                                                                                                     \
+    } while (0)
+
+// ---- the strip schedule (dist.py: StripPlan) ---------------------------------------------------------------------
+struct LevelStrip {
+    int w, h;     // size of the whole level
+    int y0, y1;   // rows this rank owns (and produces flow for)
+    int by0, by1; // rows its image buffers hold: own rows plus halo, clipped to the image
+    int cy0, cy1; // rows of the next-coarser level's cumulative flow its buffer holds
+};
+struct StripPlan {
+    int W, H, levels, win, world, reach, r, img_halo;
+    std::vector<int> coarse_bounds;
+    LevelStrip level(int k, int rank) const
+    {
+        const int sh = levels - 1 - k;
+        LevelStrip s;
+        s.w = W >> k;
+        s.h = H >> k;
+        s.y0 = coarse_bounds[rank] << sh;
+        s.y1 = rank == world - 1 ? s.h : coarse_bounds[rank + 1] << sh;
+        s.by0 = std::max(0, s.y0 - img_halo);
+        s.by1 = std::min(s.h, s.y1 + img_halo);
+        if (k < levels - 1) {
+            const int hc = H >> (k + 1);
+            // the kernel looks up cum[(y >> 1)] for the rows it warps (its packed tile: own rows -r-2 .. +r+1)
+            s.cy0 = std::max(0, (s.y0 - r - 2) >> 1);
+            s.cy1 = std::min(hc, ((s.y1 + r + 1) >> 1) + 1);
+        } else {
+            s.cy0 = s.cy1 = 0;
+        }
+        return s;
+    }
+};
+} // namespace ofb
+
+using namespace ofb;
+
+struct ofb_strips {
+    ofb_ctx *ctx = nullptr;
+    StripPlan plan;
+    int rank = 0, warp_mode = OFB_WARP_BILINEAR;
+    float flow_scale = 1.0f;
+    ncclComm_t comm = nullptr;
+    std::vector<LevelStrip> s;                 // this rank's strip per level
+    std::vector<size_t> pitch;                 // image pitch per level
+    std::vector<uint8_t *> prev, next;         // [by0, by1) rows
+    std::vector<float *> flow, cum, cum_in;    // flow / cum: buffer rows (origin by0); cum_in[k]: rows [cy0, cy1) of cum_{k+1}
+    int *overflow = nullptr;
+    std::vector<void *> allocs;
+};
+
+namespace {
+int dev_alloc(ofb_strips *st, void **p, size_t bytes)
+{
+    OFB_CUDA_TRY(cudaMalloc(p, bytes ? bytes : 16));
+    OFB_CUDA_TRY(cudaMemset(*p, 0, bytes ? bytes : 16));
+    st->allocs.push_back(*p);
+    return OFB_OK;
+}
+// rows [lo, hi) that `owner` owns and `peer`'s buffer [b0, b1) holds
+inline bool overlap(int own0, int own1, int b0, int b1, int *lo, int *hi)
+{
+    *lo = std::max(own0, b0);
+    *hi = std::min(own1, b1);
+    return *lo < *hi;
+}
+} // namespace
+
+extern "C" {
+
+int ofb_strips_nccl_unique_id(void *id128)
+{
+    NcclApi *n = nccl();
+    if (!n) {
+        set_error("libnccl.so.2 could not be loaded");
+        return OFB_ERR_UNSUPPORTED;
+    }
+    if (!id128) {
+        set_error("NULL id buffer");
+        return OFB_ERR_INVALID;
+    }
+    NcclUniqueId id;
+    OFB_NCCL_TRY(n->GetUniqueId(&id));
+    memcpy(id128, &id, sizeof id);
+    return OFB_OK;
+}
+
+int ofb_strips_create(ofb_ctx *ctx, int w, int h, int levels, int win, int warp_mode, float flow_scale, int world, int rank,
+                      int reach, const void *nccl_id128, ofb_strips **out)
+{
+    if (!ctx || !out || w < 1 || h < 1 || levels < 1 || levels > OFB_MAX_LEVELS || (win & 1) == 0 || win < 3 ||
+        win > OFB_MAX_WINDOW || world < 1 || rank < 0 || rank >= world || reach < 0) {
+        set_error("strips_create: bad arguments");
+        return OFB_ERR_INVALID;
+    }
+    if (warp_mode == OFB_WARP_AS_WRITTEN && levels > 1) {
+        set_error("OFB_WARP_AS_WRITTEN needs pixel (0,0) of every coarser level: not available on strips");
+        return OFB_ERR_UNSUPPORTED;
+    }
+    const int hc = h >> (levels - 1);
+    if (hc < world || (w >> (levels - 1)) < 1) {
+        set_error("coarsest level has %d rows, cannot cut it into %d strips", hc, world);
+        return OFB_ERR_INVALID;
+    }
+    if (world > 1 && !nccl_id128) {
+        set_error("strips_create: a NCCL unique id is required for world > 1");
+        return OFB_ERR_INVALID;
+    }
+    OFB_CUDA_TRY(cudaSetDevice(ctx_device(ctx)));
+    ofb_strips *st = new ofb_strips;
+    st->ctx = ctx;
+    st->rank = rank;
+    st->warp_mode = warp_mode;
+    st->flow_scale = flow_scale;
+    StripPlan &pl = st->plan;
+    pl.W = w, pl.H = h, pl.levels = levels, pl.win = win, pl.world = world, pl.reach = reach;
+    pl.r = win / 2;
+    // image halo: 3x3 stencil + window radius + one row of even-row alignment + warp reach + bilinear tap
+    pl.img_halo = pl.r + 2 + reach + 2;
+    for (int rk = 0; rk < world; rk++) pl.coarse_bounds.push_back((int)(((long long)rk * hc) / world));
+    pl.coarse_bounds.push_back(hc);
+    int rc = OFB_OK;
+    for (int k = 0; k < levels && rc == OFB_OK; k++) {
+        const LevelStrip s = pl.level(k, rank);
+        st->s.push_back(s);
+        const size_t pitch = ((size_t)s.w + 63) / 64 * 64;
+        st->pitch.push_back(pitch);
+        void *p = nullptr;
+        const int rows = s.by1 - s.by0;
+        if ((rc = dev_alloc(st, &p, pitch * rows))) break;
+        st->prev.push_back(static_cast<uint8_t *>(p));
+        if ((rc = dev_alloc(st, &p, pitch * rows))) break;
+        st->next.push_back(static_cast<uint8_t *>(p));
+        if ((rc = dev_alloc(st, &p, (size_t)s.w * rows * 8))) break;
+        st->flow.push_back(static_cast<float *>(p));
+        if ((rc = dev_alloc(st, &p, (size_t)s.w * rows * 8))) break;
+        st->cum.push_back(static_cast<float *>(p));
+        if ((rc = dev_alloc(st, &p, (size_t)(s.w >> 1) * std::max(s.cy1 - s.cy0, 1) * 8))) break;
+        st->cum_in.push_back(static_cast<float *>(p));
+    }
+    if (rc == OFB_OK) {
+        void *p = nullptr;
+        rc = dev_alloc(st, &p, sizeof(int));
+        st->overflow = static_cast<int *>(p);
+    }
+    if (rc == OFB_OK && world > 1) {
+        NcclApi *n = nccl();
+        if (!n) {
+            set_error("libnccl.so.2 could not be loaded");
+            rc = OFB_ERR_UNSUPPORTED;
+        } else {
+            NcclUniqueId id;
+            memcpy(&id, nccl_id128, sizeof id);
+            const int r = n->CommInitRank(&st->comm, world, id, rank);
+            if (r != NCCL_SUCCESS) {
+                set_error("ncclCommInitRank failed: %s", n->GetErrorString(r));
+                rc = OFB_ERR_CUDA;
+            }
+        }
+    }
+    if (rc != OFB_OK) {
+        for (void *p : st->allocs) cudaFree(p);
+        delete st;
+        return rc;
+    }
+    *out = st;
+    return OFB_OK;
+}
+
+int ofb_strips_destroy(ofb_strips *st)
+{
+    if (!st) return OFB_OK;
+    cudaSetDevice(ctx_device(st->ctx));
+    if (st->comm && nccl()) nccl()->CommDestroy(st->comm);
+    for (void *p : st->allocs) cudaFree(p);
+    delete st;
+    return OFB_OK;
+}
+
+int ofb_strips_own_rows(const ofb_strips *st, int level, int *y0, int *y1)
+{
+    if (!st || level < 0 || level >= st->plan.levels) {
+        set_error("strips_own_rows: bad arguments");
+        return OFB_ERR_INVALID;
+    }
+    if (y0) *y0 = st->s[level].y0;
+    if (y1) *y1 = st->s[level].y1;
+    return OFB_OK;
+}
+
+int ofb_strips_result(const ofb_strips *st, int level, float **flow_own_d, float **total_own_d)
+{
+    if (!st || level < 0 || level >= st->plan.levels) {
+        set_error("strips_result: bad arguments");
+        return OFB_ERR_INVALID;
+    }
+    const LevelStrip &s = st->s[level];
+    const size_t off = (size_t)(s.y0 - s.by0) * s.w * 2;
+    if (flow_own_d) *flow_own_d = st->flow[level] + off;
+    // cumulative flow exists where a level writes it: every level but the coarsest (whose cumulative flow is its flow)
+    if (total_own_d) *total_own_d = (level < st->plan.levels - 1 ? st->cum[level] : st->flow[level]) + off;
+    return OFB_OK;
+}
+
+// One pair: own rows of level 0 in, residual (and cumulative) flow of the own rows of every level out, all
+// asynchronous on `stream`.  prev_own_d / next_own_d: rows [y0, y1) of level 0, planar u8 with `pitch` bytes per row.
+int ofb_strips_run_device(ofb_strips *st, const uint8_t *prev_own_d, const uint8_t *next_own_d, size_t pitch, void *stream)
+{
+    if (!st || !prev_own_d || !next_own_d) {
+        set_error("strips_run: bad arguments");
+        return OFB_ERR_INVALID;
+    }
+    OFB_CUDA_TRY(cudaSetDevice(ctx_device(st->ctx)));
+    cudaStream_t q = static_cast<cudaStream_t>(stream);
+    const StripPlan &pl = st->plan;
+    NcclApi *n = pl.world > 1 ? nccl() : nullptr;
+    unsigned long long *launches = ctx_launch_counter(st->ctx);
+    const int L = pl.levels, me = st->rank;
+    if (pitch < (size_t)pl.W) {
+        set_error("strips_run: pitch %zu smaller than the width %d", pitch, pl.W);
+        return OFB_ERR_INVALID;
+    }
+    {
+        const LevelStrip &s = st->s[0];
+        const size_t off = (size_t)(s.y0 - s.by0) * st->pitch[0];
+        OFB_CUDA_TRY(cudaMemcpy2DAsync(st->prev[0] + off, st->pitch[0], prev_own_d, pitch, (size_t)s.w, (size_t)(s.y1 - s.y0),
+                                       cudaMemcpyDeviceToDevice, q));
+        OFB_CUDA_TRY(cudaMemcpy2DAsync(st->next[0] + off, st->pitch[0], next_own_d, pitch, (size_t)s.w, (size_t)(s.y1 - s.y0),
+                                       cudaMemcpyDeviceToDevice, q));
+    }
+    OFB_CUDA_TRY(cudaMemsetAsync(st->overflow, 0, sizeof(int), q));
+    // pyramid: level-k halo exchange (rows each neighbour owns), then level k+1 own rows from level k own rows +- 1
+    for (int k = 0; k < L; k++) {
+        const LevelStrip &s = st->s[k];
+        const size_t P = st->pitch[k];
+        if (n) {
+            OFB_NCCL_TRY(n->GroupStart());
+            for (int peer = 0; peer < pl.world; peer++) {
+                if (peer == me) continue;
+                const LevelStrip ps = pl.level(k, peer);
+                int lo, hi;
+                if (overlap(s.y0, s.y1, ps.by0, ps.by1, &lo, &hi)) { // my rows the peer's buffer holds
+                    OFB_NCCL_TRY(n->Send(st->prev[k] + (size_t)(lo - s.by0) * P, (size_t)(hi - lo) * P, NCCL_UINT8, peer, st->comm, q));
+                    OFB_NCCL_TRY(n->Send(st->next[k] + (size_t)(lo - s.by0) * P, (size_t)(hi - lo) * P, NCCL_UINT8, peer, st->comm, q));
+                }
+                if (overlap(ps.y0, ps.y1, s.by0, s.by1, &lo, &hi)) { // the peer's rows my buffer holds
+                    OFB_NCCL_TRY(n->Recv(st->prev[k] + (size_t)(lo - s.by0) * P, (size_t)(hi - lo) * P, NCCL_UINT8, peer, st->comm, q));
+                    OFB_NCCL_TRY(n->Recv(st->next[k] + (size_t)(lo - s.by0) * P, (size_t)(hi - lo) * P, NCCL_UINT8, peer, st->comm, q));
+                }
+            }
+            OFB_NCCL_TRY(n->GroupEnd());
+        }
+        if (k + 1 < L) {
+            const LevelStrip &d = st->s[k + 1];
+            const size_t PD = st->pitch[k + 1];
+            for (uint8_t *const *buf : {st->prev.data(), st->next.data()}) {
+                int rc = launch_pyr_down_strip(buf[k], P, s.w, s.by1 - s.by0, s.by0, buf[k + 1] + (size_t)(d.y0 - d.by0) * PD, PD,
+                                               d.y0, d.y1, q, launches);
+                if (rc) return rc;
+            }
+        }
+    }
+    // coarse to fine: rows [cy0, cy1) of cum_{k+1} into cum_in[k] (own part copied, the rest received), then the level
+    for (int k = L - 1; k >= 0; k--) {
+        const LevelStrip &s = st->s[k];
+        if (k < L - 1) {
+            const LevelStrip &up = st->s[k + 1];
+            const float *src = (k + 1 < L - 1) ? st->cum[k + 1] : st->flow[k + 1]; // cum of the coarsest level is its flow
+            const size_t rowf = (size_t)up.w * 2;                                  // floats per row
+            int lo, hi;
+            if (overlap(up.y0, up.y1, s.cy0, s.cy1, &lo, &hi))
+                OFB_CUDA_TRY(cudaMemcpyAsync(st->cum_in[k] + (size_t)(lo - s.cy0) * rowf, src + (size_t)(lo - up.by0) * rowf,
+                                             (size_t)(hi - lo) * rowf * 4, cudaMemcpyDeviceToDevice, q));
+            if (n) {
+                OFB_NCCL_TRY(n->GroupStart());
+                for (int peer = 0; peer < pl.world; peer++) {
+                    if (peer == me) continue;
+                    const LevelStrip pk = pl.level(k, peer), pu = pl.level(k + 1, peer);
+                    if (overlap(up.y0, up.y1, pk.cy0, pk.cy1, &lo, &hi)) // my cum rows the peer needs
+                        OFB_NCCL_TRY(n->Send(src + (size_t)(lo - up.by0) * rowf, (size_t)(hi - lo) * rowf * 4, NCCL_UINT8, peer, st->comm, q));
+                    if (overlap(pu.y0, pu.y1, s.cy0, s.cy1, &lo, &hi)) // the peer's cum rows I need
+                        OFB_NCCL_TRY(n->Recv(st->cum_in[k] + (size_t)(lo - s.cy0) * rowf, (size_t)(hi - lo) * rowf * 4, NCCL_UINT8, peer,
+                                             st->comm, q));
+                }
+                OFB_NCCL_TRY(n->GroupEnd());
+            }
+        }
+        LkLevelArgs a{};
+        a.prev = st->prev[k];
+        a.next = st->next[k];
+        a.pitch = st->pitch[k];
+        a.image_stride = a.pitch * (size_t)(s.by1 - s.by0);
+        a.w = s.w;
+        a.h_local = s.by1 - s.by0;
+        a.y_off = s.by0;
+        a.h_global = s.h;
+        a.out_y0 = s.y0 - s.by0;
+        a.out_y1 = s.y1 - s.by0;
+        a.n_pairs = 1;
+        a.win = pl.win;
+        a.warp_mode = st->warp_mode;
+        a.flow_scale = st->flow_scale;
+        a.cum_in = k < L - 1 ? st->cum_in[k] : nullptr;
+        a.cum_w = s.w >> 1;
+        a.cum_h_global = s.h >> 1;
+        a.cum_y_off = s.cy0;
+        a.cum_h_local = std::max(s.cy1 - s.cy0, 1);
+        a.cum_pair_stride = 0;
+        a.flow_out = st->flow[k];
+        const bool want_cum = (k > 0 && k < L - 1) || (k == 0 && L > 1);
+        a.cum_out = want_cum ? st->cum[k] : nullptr;
+        a.flow_pair_stride = 0;
+        a.reach_overflow = st->overflow;
+        a.sm_count = ctx_sm_count(st->ctx);
+        int rc = launch_lk_level(a, q, launches);
+        if (rc) return rc;
+    }
+    return OFB_OK;
+}
+
+// Synchronises the stream and reports whether a warp sample reached past the exchanged halo rows (the result is
+// then NOT the whole-frame result: raise `reach`).
+int ofb_strips_check(ofb_strips *st, void *stream, int *overflow)
+{
+    if (!st) {
+        set_error("strips_check: NULL handle");
+        return OFB_ERR_INVALID;
+    }
+    OFB_CUDA_TRY(cudaSetDevice(ctx_device(st->ctx)));
+    int v = 0;
+    OFB_CUDA_TRY(cudaMemcpyAsync(&v, st->overflow, sizeof(int), cudaMemcpyDeviceToHost, static_cast<cudaStream_t>(stream)));
+    OFB_CUDA_TRY(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
+    if (overflow) *overflow = v;
+    return OFB_OK;
+}
+
+} // extern "C"

@@ -374,6 +374,86 @@ class StripRunner:
         return src[s.y0 - s.by0:s.y1 - s.by0]
 
 
+class NativeStrips:
+    """The native row-strip runner (csrc/strips.cu): the same schedule as StripRunner, but a whole pair is enqueued
+    from C++ on one stream and the halo rows move by NCCL send/recv between the ranks' buffers.  `torch.distributed`
+    is used once, to hand rank 0's NCCL unique id to the other ranks."""
+
+    def __init__(self, ctx, w: int, h: int, levels: int, win: int, world: int, rank: int, device, warp_mode: int = WARP_BILINEAR,
+                 flow_scale: float = 1.0, reach: int = 16):
+        import ctypes as C
+
+        import torch
+
+        from . import _lib as L
+
+        self.torch, self.C, self.L, self.lib, self.ctx = torch, C, L, L.load(), ctx
+        self.w, self.h, self.levels, self.dev = w, h, levels, device
+        idbuf = torch.zeros(128, dtype=torch.uint8)
+        if world > 1:
+            import torch.distributed as dist
+
+            if rank == 0:
+                raw = (C.c_ubyte * 128)()
+                L.check(self.lib.ofb_strips_nccl_unique_id(C.cast(raw, C.c_void_p)))
+                idbuf = torch.tensor(list(raw), dtype=torch.uint8)
+            idbuf = idbuf.to(device)
+            dist.broadcast(idbuf, 0)
+        raw = (C.c_ubyte * 128)(*idbuf.cpu().tolist())
+        hnd = C.c_void_p()
+        L.check(self.lib.ofb_strips_create(ctx._h, w, h, levels, win, warp_mode, C.c_float(flow_scale), world, rank, reach,
+                                           C.cast(raw, C.c_void_p) if world > 1 else None, C.byref(hnd)))
+        self._h = hnd
+
+    def own_rows(self, level: int = 0):
+        y0, y1 = self.C.c_int(), self.C.c_int()
+        self.L.check(self.lib.ofb_strips_own_rows(self._h, level, self.C.byref(y0), self.C.byref(y1)))
+        return y0.value, y1.value
+
+    def run(self, prev_own, next_own, stream: int = 0) -> None:
+        """prev_own / next_own: (own_rows, pitch) uint8 CUDA tensors (or row-sliced views) of level 0."""
+        self.L.check(self.lib.ofb_strips_run_device(self._h, prev_own.data_ptr(), next_own.data_ptr(), prev_own.stride(0),
+                                                    self.C.c_void_p(stream)))
+
+    def check(self, stream: int = 0) -> None:
+        v = self.C.c_int()
+        self.L.check(self.lib.ofb_strips_check(self._h, self.C.c_void_p(stream), self.C.byref(v)))
+        if v.value:
+            raise RuntimeError("a warp sample reached past the exchanged halo rows: raise `reach`")
+
+    def own_flow(self, level: int, total: bool = False):
+        """A torch view (no copy) of the own rows of the residual (or cumulative) flow of `level`."""
+        f, t = self.C.c_void_p(), self.C.c_void_p()
+        self.L.check(self.lib.ofb_strips_result(self._h, level, self.C.byref(f), self.C.byref(t)))
+        y0, y1 = self.own_rows(level)
+        n = (y1 - y0) * (self.w >> level) * 2
+        ptr = t.value if total else f.value
+        return _device_view(self.torch, ptr, (y1 - y0, self.w >> level, 2), self.dev)
+
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            self.lib.ofb_strips_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def _device_view(torch, ptr: int, shape, device):
+    """float32 torch tensor over device memory owned by the library (valid while its owner lives)."""
+    n = 1
+    for d in shape:
+        n *= d
+
+    class _Holder:
+        __cuda_array_interface__ = {"shape": (n,), "typestr": "<f4", "data": (ptr, False), "version": 3}
+
+    return torch.as_tensor(_Holder(), device=device).view(*shape)
+
+
 def run_strips_local(ctx, prev0, next0, levels: int, win: int, world: int, warp_mode: int = WARP_BILINEAR,
                      flow_scale: float = 1.0, reach: int = 16):
     """Emulate `world` ranks on ONE device: the same StripRunner code, with every halo exchange done

@@ -193,6 +193,27 @@ int ofb_stream_push_bgr_host(ofb_stream *s, const unsigned char *frame_bgr, floa
                              float *total_flow_h, int *has_flow);
 int ofb_stream_destroy(ofb_stream *s);
 
+/* ---- row strips of one large pair over several GPUs (BASELINE configs[4]); the reference is single-GPU ----------
+ * One process per GPU, one handle per process.  The schedule (strip bounds fixed on the coarsest level and doubled
+ * per finer level; per level the neighbours' image halo rows and the next-coarser cumulative-flow rows) is that of
+ * cuda_optical_flow_2_b200/dist.py; here a whole pair is enqueued on one stream without host synchronisation and
+ * the halo rows move by NCCL send/recv between the ranks' buffers (libnccl.so.2 is opened on first use; it is not
+ * a link-time dependency).  The result is bit-identical to the whole-frame result unless ofb_strips_check reports
+ * that a warp sample reached past the exchanged rows (`reach`, in rows of the level being warped).
+ *   ofb_strips_nccl_unique_id : rank 0 makes the 128-byte id, the application broadcasts it (any transport)
+ *   ofb_strips_create         : collective over all ranks (ncclCommInitRank)
+ *   ofb_strips_run_device     : prev_own_d / next_own_d = rows [y0, y1) of level 0 (ofb_strips_own_rows), planar u8
+ *   ofb_strips_result         : device pointers to the own rows of the residual flow / cumulative flow of a level */
+typedef struct ofb_strips ofb_strips;
+int ofb_strips_nccl_unique_id(void *id128);
+int ofb_strips_create(ofb_ctx *ctx, int w, int h, int levels, int win, int warp_mode, float flow_scale, int world, int rank,
+                      int reach, const void *nccl_id128, ofb_strips **out);
+int ofb_strips_own_rows(const ofb_strips *s, int level, int *y0, int *y1);
+int ofb_strips_run_device(ofb_strips *s, const uint8_t *prev_own_d, const uint8_t *next_own_d, size_t pitch, void *stream);
+int ofb_strips_result(const ofb_strips *s, int level, float **flow_own_d, float **total_own_d);
+int ofb_strips_check(ofb_strips *s, void *stream, int *overflow);
+int ofb_strips_destroy(ofb_strips *s);
+
 /* ---- debug derivative views: showTest (main.cu:19-92) without the windows ------------------------------------------
  * ofb_conv_3ch_1ch_u8_u8_host replaces gpu::conv_3ch_1ch_tiled (OptFlowGpu.cuh; OptFlowGpu.cu:741-766, kernel
  *   :380-423): 3-channel u8 in (channel 0 is read), u8 out; an int accumulator truncated after every tap, result

@@ -11,7 +11,7 @@ import torch
 import torch.distributed as dist
 from bench import synth_pairs_torch
 from cuda_optical_flow_2_b200 import Context, WARP_BILINEAR
-from cuda_optical_flow_2_b200.dist import DistTransport, GatherTransport, StripPlan, StripRunner
+from cuda_optical_flow_2_b200.dist import DistTransport, GatherTransport, NativeStrips, StripPlan, StripRunner
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--w", type=int, default=7680); ap.add_argument("--h", type=int, default=4320)
@@ -19,6 +19,7 @@ ap.add_argument("--levels", type=int, default=4); ap.add_argument("--win", type=
 ap.add_argument("--reps", type=int, default=10); ap.add_argument("--reach", type=int, default=16)
 ap.add_argument("--check", action="store_true")
 ap.add_argument("--transport", default="gather", choices=["gather", "p2p"], help="halo exchange: one all-gather per exchange (graph-capturable) or grouped send/recv")
+ap.add_argument("--native", action="store_true", help="the native runner (csrc/strips.cu: C++ host side, NCCL send/recv between the ranks' buffers)")
 ap.add_argument("--graph", action="store_true", help="capture one pair in a CUDA graph and replay it (1 GPU: works, -8 %; with NCCL exchanges the capture hung on this stack, PyTorch 2.11 + NCCL 2.28: unresolved)")
 a = ap.parse_args()
 world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0")); local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -42,14 +43,19 @@ else:
 rn = StripRunner(ctx, plan, rank, tp, dev, WARP_BILINEAR)
 s0 = rn.strips[0]
 pr, nr = prev[0, s0.y0:s0.y1, :a.w], nxt[0, s0.y0:s0.y1, :a.w]
+nat = NativeStrips(ctx, a.w, a.h, a.levels, a.win, world, rank, dev, WARP_BILINEAR, 1.0, a.reach) if a.native else None
 def one():
-    rn.step(pr, nr)
+    if nat is not None:
+        nat.run(prev[0, s0.y0:s0.y1], nxt[0, s0.y0:s0.y1], torch.cuda.current_stream(dev).cuda_stream)
+    else:
+        rn.step(pr, nr)
 side = torch.cuda.Stream(dev)
 side.wait_stream(torch.cuda.current_stream(dev))
 with torch.cuda.stream(side):
     rn.use_current_stream()
     for _ in range(3): one()
-    rn.check_overflow()
+    if nat is not None: nat.check(torch.cuda.current_stream(dev).cuda_stream)
+    else: rn.check_overflow()
     if a.graph:
         torch.cuda.synchronize()
         g = torch.cuda.CUDAGraph()
@@ -78,7 +84,7 @@ if a.check:
     ok = True
     for k in range(a.levels):
         s = rn.strips[k]
-        ref, got = whole[k][0, s.y0:s.y1], rn.own_flow(k)
+        ref, got = whole[k][0, s.y0:s.y1], (nat.own_flow(k) if nat is not None else rn.own_flow(k))
         m = ~torch.isnan(ref)
         ok &= bool(torch.equal(torch.isnan(ref), torch.isnan(got)) and torch.equal(ref[m], got[m]))
     f = torch.tensor([1 if ok else 0], device=dev)
@@ -89,5 +95,5 @@ if rank == 0:
            sum((hi - lo) * (a.w >> (k + 1)) * 8 for k in range(a.levels) for _, lo, hi, _ in plan.cum_messages(k, 0))
     print(json.dumps({"mode": "row-strips", "w": a.w, "h": a.h, "levels": a.levels, "win": a.win, "n_gpus": world,
                       "ms_per_pair": t.item(), "mpx_pairs_per_s": a.w * a.h / 1e6 / (t.item() / 1e3),
-                      "bit_identical_to_whole_frame": ok, "cuda_graph": bool(a.graph), "transport": a.transport if world > 1 else None, "halo_bytes_sent_rank0_per_pair": halo}), flush=True)
+                      "bit_identical_to_whole_frame": ok, "cuda_graph": bool(a.graph), "native": bool(a.native), "transport": a.transport if world > 1 else None, "halo_bytes_sent_rank0_per_pair": halo}), flush=True)
 if world > 1: dist.destroy_process_group()
