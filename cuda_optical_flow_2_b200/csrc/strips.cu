@@ -5,8 +5,9 @@
 // cumulative-flow halo), but here the whole pair -- own-row upload, per-level halo exchange, pyramid, fused level
 // kernels -- is enqueued on one CUDA stream from C++ with no host synchronisation, and the halo rows move by NCCL
 // send/recv (NVLink / NVSwitch) straight between the ranks' image and flow buffers: rows are contiguous, so there
-// is no staging copy.  The Python StripRunner does the same through torch and is exchange-latency bound (seven
-// exchanges per pair at ~100 us of host work each); this path costs a few microseconds of host work per operation.
+// is no staging copy.  Only level-0 image rows are exchanged (the coarser levels' halo rows are rebuilt locally), so a
+// pair of L levels costs L exchanges: one for the images, L-1 for the cumulative flow.  The Python StripRunner runs
+// the 2L-1-exchange form of the schedule through torch and is bound by ~100 us of host work per exchange.
 //
 // NCCL is not a link-time dependency of the library: libnccl.so.2 is opened on first use (inside a torch process
 // that is the copy torch already loaded), and every symbol is resolved with dlsym.
@@ -82,8 +83,9 @@ static NcclApi *nccl()
 struct LevelStrip {
     int w, h;     // size of the whole level
     int y0, y1;   // rows this rank owns (and produces flow for)
-    int by0, by1; // rows its image buffers hold: own rows plus halo, clipped to the image
+    int by0, by1; // rows the level kernel needs: own rows plus halo, clipped to the image
     int cy0, cy1; // rows of the next-coarser level's cumulative flow its buffer holds
+    int eb0, eb1; // rows its image buffers hold: [by0, by1) plus what building [eb0, eb1) of the next level takes
 };
 struct StripPlan {
     int W, H, levels, win, world, reach, r, img_halo;
@@ -106,7 +108,24 @@ struct StripPlan {
         } else {
             s.cy0 = s.cy1 = 0;
         }
+        s.eb0 = s.by0;
+        s.eb1 = s.by1;
         return s;
+    }
+    // Every level of one rank.  Only level-0 rows are exchanged; the halo rows of the coarser levels are built
+    // locally (each rank repeats a few rows of pyramid work instead of three more exchanges), so a level's buffer
+    // also holds the rows 2y-1 .. 2y+1 under every row y of the next level's buffer.
+    std::vector<LevelStrip> strips(int rank) const
+    {
+        std::vector<LevelStrip> v(levels);
+        for (int k = levels - 1; k >= 0; k--) {
+            v[k] = level(k, rank);
+            if (k + 1 < levels) {
+                v[k].eb0 = std::min(v[k].by0, std::max(0, 2 * v[k + 1].eb0 - 1));
+                v[k].eb1 = std::max(v[k].by1, std::min(v[k].h, 2 * (v[k + 1].eb1 - 1) + 2));
+            }
+        }
+        return v;
     }
 };
 } // namespace ofb
@@ -120,9 +139,10 @@ struct ofb_strips {
     float flow_scale = 1.0f;
     ncclComm_t comm = nullptr;
     std::vector<LevelStrip> s;                 // this rank's strip per level
+    std::vector<LevelStrip> peer0;             // every rank's level-0 strip (for the one image exchange)
     std::vector<size_t> pitch;                 // image pitch per level
-    std::vector<uint8_t *> prev, next;         // [by0, by1) rows
-    std::vector<float *> flow, cum, cum_in;    // flow / cum: buffer rows (origin by0); cum_in[k]: rows [cy0, cy1) of cum_{k+1}
+    std::vector<uint8_t *> prev, next;         // [eb0, eb1) rows
+    std::vector<float *> flow, cum, cum_in;    // flow / cum: buffer rows (origin eb0); cum_in[k]: rows [cy0, cy1) of cum_{k+1}
     int *overflow = nullptr;
     std::vector<void *> allocs;
 };
@@ -198,13 +218,14 @@ int ofb_strips_create(ofb_ctx *ctx, int w, int h, int levels, int win, int warp_
     for (int rk = 0; rk < world; rk++) pl.coarse_bounds.push_back((int)(((long long)rk * hc) / world));
     pl.coarse_bounds.push_back(hc);
     int rc = OFB_OK;
+    st->s = pl.strips(rank);
+    for (int peer = 0; peer < world; peer++) st->peer0.push_back(pl.strips(peer)[0]);
     for (int k = 0; k < levels && rc == OFB_OK; k++) {
-        const LevelStrip s = pl.level(k, rank);
-        st->s.push_back(s);
+        const LevelStrip s = st->s[k];
         const size_t pitch = ((size_t)s.w + 63) / 64 * 64;
         st->pitch.push_back(pitch);
         void *p = nullptr;
-        const int rows = s.by1 - s.by0;
+        const int rows = s.eb1 - s.eb0;
         if ((rc = dev_alloc(st, &p, pitch * rows))) break;
         st->prev.push_back(static_cast<uint8_t *>(p));
         if ((rc = dev_alloc(st, &p, pitch * rows))) break;
@@ -273,7 +294,7 @@ int ofb_strips_result(const ofb_strips *st, int level, float **flow_own_d, float
         return OFB_ERR_INVALID;
     }
     const LevelStrip &s = st->s[level];
-    const size_t off = (size_t)(s.y0 - s.by0) * s.w * 2;
+    const size_t off = (size_t)(s.y0 - s.eb0) * s.w * 2;
     if (flow_own_d) *flow_own_d = st->flow[level] + off;
     // cumulative flow exists where a level writes it: every level but the coarsest (whose cumulative flow is its flow)
     if (total_own_d) *total_own_d = (level < st->plan.levels - 1 ? st->cum[level] : st->flow[level]) + off;
@@ -300,42 +321,40 @@ int ofb_strips_run_device(ofb_strips *st, const uint8_t *prev_own_d, const uint8
     }
     {
         const LevelStrip &s = st->s[0];
-        const size_t off = (size_t)(s.y0 - s.by0) * st->pitch[0];
+        const size_t off = (size_t)(s.y0 - s.eb0) * st->pitch[0];
         OFB_CUDA_TRY(cudaMemcpy2DAsync(st->prev[0] + off, st->pitch[0], prev_own_d, pitch, (size_t)s.w, (size_t)(s.y1 - s.y0),
                                        cudaMemcpyDeviceToDevice, q));
         OFB_CUDA_TRY(cudaMemcpy2DAsync(st->next[0] + off, st->pitch[0], next_own_d, pitch, (size_t)s.w, (size_t)(s.y1 - s.y0),
                                        cudaMemcpyDeviceToDevice, q));
     }
     OFB_CUDA_TRY(cudaMemsetAsync(st->overflow, 0, sizeof(int), q));
-    // pyramid: level-k halo exchange (rows each neighbour owns), then level k+1 own rows from level k own rows +- 1
-    for (int k = 0; k < L; k++) {
-        const LevelStrip &s = st->s[k];
-        const size_t P = st->pitch[k];
-        if (n) {
-            OFB_NCCL_TRY(n->GroupStart());
-            for (int peer = 0; peer < pl.world; peer++) {
-                if (peer == me) continue;
-                const LevelStrip ps = pl.level(k, peer);
-                int lo, hi;
-                if (overlap(s.y0, s.y1, ps.by0, ps.by1, &lo, &hi)) { // my rows the peer's buffer holds
-                    OFB_NCCL_TRY(n->Send(st->prev[k] + (size_t)(lo - s.by0) * P, (size_t)(hi - lo) * P, NCCL_UINT8, peer, st->comm, q));
-                    OFB_NCCL_TRY(n->Send(st->next[k] + (size_t)(lo - s.by0) * P, (size_t)(hi - lo) * P, NCCL_UINT8, peer, st->comm, q));
-                }
-                if (overlap(ps.y0, ps.y1, s.by0, s.by1, &lo, &hi)) { // the peer's rows my buffer holds
-                    OFB_NCCL_TRY(n->Recv(st->prev[k] + (size_t)(lo - s.by0) * P, (size_t)(hi - lo) * P, NCCL_UINT8, peer, st->comm, q));
-                    OFB_NCCL_TRY(n->Recv(st->next[k] + (size_t)(lo - s.by0) * P, (size_t)(hi - lo) * P, NCCL_UINT8, peer, st->comm, q));
-                }
+    // ONE image exchange, on level 0: the rows of my buffer that other ranks own (and vice versa), in place
+    if (n) {
+        const LevelStrip &s = st->s[0];
+        const size_t P = st->pitch[0];
+        OFB_NCCL_TRY(n->GroupStart());
+        for (int peer = 0; peer < pl.world; peer++) {
+            if (peer == me) continue;
+            const LevelStrip &ps = st->peer0[peer];
+            int lo, hi;
+            if (overlap(s.y0, s.y1, ps.eb0, ps.eb1, &lo, &hi)) { // my rows the peer's buffer holds
+                OFB_NCCL_TRY(n->Send(st->prev[0] + (size_t)(lo - s.eb0) * P, (size_t)(hi - lo) * P, NCCL_UINT8, peer, st->comm, q));
+                OFB_NCCL_TRY(n->Send(st->next[0] + (size_t)(lo - s.eb0) * P, (size_t)(hi - lo) * P, NCCL_UINT8, peer, st->comm, q));
             }
-            OFB_NCCL_TRY(n->GroupEnd());
+            if (overlap(ps.y0, ps.y1, s.eb0, s.eb1, &lo, &hi)) { // the peer's rows my buffer holds
+                OFB_NCCL_TRY(n->Recv(st->prev[0] + (size_t)(lo - s.eb0) * P, (size_t)(hi - lo) * P, NCCL_UINT8, peer, st->comm, q));
+                OFB_NCCL_TRY(n->Recv(st->next[0] + (size_t)(lo - s.eb0) * P, (size_t)(hi - lo) * P, NCCL_UINT8, peer, st->comm, q));
+            }
         }
-        if (k + 1 < L) {
-            const LevelStrip &d = st->s[k + 1];
-            const size_t PD = st->pitch[k + 1];
-            for (uint8_t *const *buf : {st->prev.data(), st->next.data()}) {
-                int rc = launch_pyr_down_strip(buf[k], P, s.w, s.by1 - s.by0, s.by0, buf[k + 1] + (size_t)(d.y0 - d.by0) * PD, PD,
-                                               d.y0, d.y1, q, launches);
-                if (rc) return rc;
-            }
+        OFB_NCCL_TRY(n->GroupEnd());
+    }
+    // pyramid: every buffer row of level k+1 from the buffer rows of level k (halo rows are built locally)
+    for (int k = 0; k + 1 < L; k++) {
+        const LevelStrip &s = st->s[k], &d = st->s[k + 1];
+        for (uint8_t *const *buf : {st->prev.data(), st->next.data()}) {
+            int rc = launch_pyr_down_strip(buf[k], st->pitch[k], s.w, s.eb1 - s.eb0, s.eb0, buf[k + 1], st->pitch[k + 1], d.eb0, d.eb1, q,
+                                           launches);
+            if (rc) return rc;
         }
     }
     // coarse to fine: rows [cy0, cy1) of cum_{k+1} into cum_in[k] (own part copied, the rest received), then the level
@@ -347,7 +366,7 @@ int ofb_strips_run_device(ofb_strips *st, const uint8_t *prev_own_d, const uint8
             const size_t rowf = (size_t)up.w * 2;                                  // floats per row
             int lo, hi;
             if (overlap(up.y0, up.y1, s.cy0, s.cy1, &lo, &hi))
-                OFB_CUDA_TRY(cudaMemcpyAsync(st->cum_in[k] + (size_t)(lo - s.cy0) * rowf, src + (size_t)(lo - up.by0) * rowf,
+                OFB_CUDA_TRY(cudaMemcpyAsync(st->cum_in[k] + (size_t)(lo - s.cy0) * rowf, src + (size_t)(lo - up.eb0) * rowf,
                                              (size_t)(hi - lo) * rowf * 4, cudaMemcpyDeviceToDevice, q));
             if (n) {
                 OFB_NCCL_TRY(n->GroupStart());
@@ -355,7 +374,7 @@ int ofb_strips_run_device(ofb_strips *st, const uint8_t *prev_own_d, const uint8
                     if (peer == me) continue;
                     const LevelStrip pk = pl.level(k, peer), pu = pl.level(k + 1, peer);
                     if (overlap(up.y0, up.y1, pk.cy0, pk.cy1, &lo, &hi)) // my cum rows the peer needs
-                        OFB_NCCL_TRY(n->Send(src + (size_t)(lo - up.by0) * rowf, (size_t)(hi - lo) * rowf * 4, NCCL_UINT8, peer, st->comm, q));
+                        OFB_NCCL_TRY(n->Send(src + (size_t)(lo - up.eb0) * rowf, (size_t)(hi - lo) * rowf * 4, NCCL_UINT8, peer, st->comm, q));
                     if (overlap(pu.y0, pu.y1, s.cy0, s.cy1, &lo, &hi)) // the peer's cum rows I need
                         OFB_NCCL_TRY(n->Recv(st->cum_in[k] + (size_t)(lo - s.cy0) * rowf, (size_t)(hi - lo) * rowf * 4, NCCL_UINT8, peer,
                                              st->comm, q));
@@ -367,13 +386,13 @@ int ofb_strips_run_device(ofb_strips *st, const uint8_t *prev_own_d, const uint8
         a.prev = st->prev[k];
         a.next = st->next[k];
         a.pitch = st->pitch[k];
-        a.image_stride = a.pitch * (size_t)(s.by1 - s.by0);
+        a.image_stride = a.pitch * (size_t)(s.eb1 - s.eb0);
         a.w = s.w;
-        a.h_local = s.by1 - s.by0;
-        a.y_off = s.by0;
+        a.h_local = s.eb1 - s.eb0;
+        a.y_off = s.eb0;
         a.h_global = s.h;
-        a.out_y0 = s.y0 - s.by0;
-        a.out_y1 = s.y1 - s.by0;
+        a.out_y0 = s.y0 - s.eb0;
+        a.out_y1 = s.y1 - s.eb0;
         a.n_pairs = 1;
         a.win = pl.win;
         a.warp_mode = st->warp_mode;
