@@ -186,3 +186,32 @@ def test_config4_8k_strips_equal_whole_frame(ctx, oracle):
         ref = whole[k][0]
         m = ~torch.isnan(ref)
         assert torch.equal(torch.isnan(got), torch.isnan(ref)) and torch.equal(got[m], ref[m]), f"level {k}"
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("W,H,levels,win", [(640, 480, 3, 9), (322, 406, 2, 5), (1920, 1080, 4, 15)])
+def test_native_strip_runner_world_one_equals_whole_frame(ctx, oracle, W, H, levels, win):
+    """csrc/strips.cu on a single rank (no exchange): own-row upload, locally built pyramid, strip variants of the
+    kernels -- bit for bit the whole-frame result.  (The multi-rank exchange is exercised by scripts/run_strips.py
+    --native under torchrun; its schedule is the one the gloo tests above check.)"""
+    import torch
+
+    from cuda_optical_flow_2_b200 import WARP_BILINEAR, planar_to_device
+    from cuda_optical_flow_2_b200.dist import NativeStrips
+
+    prev = oracle.make_frame(W, H, 0, 0, 8, 321)
+    nxt = oracle.make_frame(W, H, 2.25, -1.5, 8, 321)
+    dp, dn = planar_to_device(prev[None]), planar_to_device(nxt[None])
+    whole = ctx.flow_pairs_device(dp, dn, W, levels, win, warp_mode=WARP_BILINEAR)
+    ns = NativeStrips(ctx, W, H, levels, win, 1, 0, torch.device("cuda", 0), WARP_BILINEAR, 1.0, 16)
+    try:
+        assert ns.own_rows(0) == (0, H)
+        st = torch.cuda.current_stream().cuda_stream
+        ns.run(dp[0], dn[0], st)
+        ns.check(st)
+        for k in range(levels):
+            ref, got = whole[k][0], ns.own_flow(k)
+            m = ~torch.isnan(ref)
+            assert torch.equal(torch.isnan(ref), torch.isnan(got)) and torch.equal(ref[m], got[m]), f"level {k}"
+    finally:
+        ns.close()
