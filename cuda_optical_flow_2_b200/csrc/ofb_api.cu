@@ -23,7 +23,7 @@ static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; 
 
 } // namespace ofb
 
-#define OFB_LANES 2
+#define OFB_LANES 3
 
 // One growable device workspace per context; carved by offset for each call.  Growing it frees the
 // old block (cudaFree synchronises the device), so steady-state calls allocate nothing -- unlike
@@ -798,8 +798,10 @@ int ofb_flow_pairs_host(ofb_ctx *c, const ofb_params *p, const unsigned char *pr
     OFB_GUARD(c);
     // Software pipeline over sub-batches on OFB_LANES streams: while one lane downloads its flow the
     // other uploads and computes, so the PCIe directions and the SMs overlap (with pinned host memory).
+    // Sub-batches are kept small (at least eight per lane when the batch allows): the first upload and the last
+    // download are the part of the pipeline nothing overlaps, and a 1080p pair already is 12 MB in and 22 MB out.
     const int n = p->n_pairs;
-    int sub = n / (2 * OFB_LANES);
+    int sub = n / (8 * OFB_LANES);
     if (sub < 1) sub = 1;
     if (sub > 8) sub = 8;
     ofb_params ps = *p;
