@@ -80,6 +80,10 @@ SIGNATURES = {
     "ofb_strips_result": (C.c_int, [_vp, C.c_int, C.POINTER(_vp), C.POINTER(_vp)]),
     "ofb_strips_check": (C.c_int, [_vp, _vp, i32p]),
     "ofb_strips_destroy": (C.c_int, [_vp]),
+    "ofb_strips_peer_handle": (C.c_int, [_vp, _vp]),
+    "ofb_strips_peer_connect": (C.c_int, [_vp, _vp]),
+    "ofb_strips_peer_arena": (C.c_int, [_vp, C.POINTER(_vp)]),
+    "ofb_strips_peer_connect_local": (C.c_int, [_vp, C.POINTER(_vp)]),
     "ofb_conv_3ch_1ch_u8_u8_host": (C.c_int, [_vp, u8p, C.c_int, C.c_int, u8p, f32p, C.c_int, C.c_int]),
     "ofb_debug_view_host_u8c3": (C.c_int, [_vp, u8p, u8p, C.c_int, C.c_int, C.c_int, C.c_int, u8p]),
     "ofb_compose_flow_host": (C.c_int, [_vp, C.POINTER(f32p), C.c_int, C.c_int, C.c_int, C.c_int, f32p]),

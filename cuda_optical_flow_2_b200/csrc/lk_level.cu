@@ -124,4 +124,21 @@ int launch_lk_level(const LkLevelArgs &a, cudaStream_t stream, unsigned long lon
     }
 }
 
+template <int WIN> int preload_lk_win(); // lk_win.cu
+int preload_lk_level(int win)
+{
+    switch (win) {
+    case 3: return preload_lk_win<3>();
+    case 5: return preload_lk_win<5>();
+    case 7: return preload_lk_win<7>();
+    case 9: return preload_lk_win<9>();
+    case 11: return preload_lk_win<11>();
+    case 13: return preload_lk_win<13>();
+    case 15: return preload_lk_win<15>();
+    case 17: return preload_lk_win<17>();
+    case 19: return preload_lk_win<19>();
+    default: set_error("lk_level: window %d not supported (odd 3..19)", win); return OFB_ERR_UNSUPPORTED;
+    }
+}
+
 } // namespace ofb

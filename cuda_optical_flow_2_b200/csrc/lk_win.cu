@@ -115,4 +115,19 @@ template <int WIN> int launch_lk_win(const LkLevelArgs &a, cudaStream_t s, unsig
 
 template int launch_lk_win<LK_WIN>(const LkLevelArgs &a, cudaStream_t s, unsigned long long *l);
 
+// Loads every variant of this window's kernel now (CUDA loads kernels lazily, and loading may synchronise the context:
+// a launch that first has to load its kernel can then not be enqueued behind a kernel that spins on a neighbour).
+template <int WIN> int preload_lk_win()
+{
+    cudaFuncAttributes fa;
+    OFB_CUDA_TRY(cudaFuncGetAttributes(&fa, lk_level_kernel<WIN, 0, false>));
+    OFB_CUDA_TRY(cudaFuncGetAttributes(&fa, lk_level_kernel<WIN, 0, true>));
+    OFB_CUDA_TRY(cudaFuncGetAttributes(&fa, lk_level_kernel<WIN, 1, false>));
+    OFB_CUDA_TRY(cudaFuncGetAttributes(&fa, lk_level_kernel<WIN, 1, true>));
+    OFB_CUDA_TRY(cudaFuncGetAttributes(&fa, lk_level_kernel<WIN, 2, false>));
+    OFB_CUDA_TRY(cudaFuncGetAttributes(&fa, lk_level_kernel<WIN, 2, true>));
+    return OFB_OK;
+}
+template int preload_lk_win<LK_WIN>();
+
 } // namespace ofb

@@ -47,6 +47,8 @@ struct LkLevelArgs {
     int sm_count;
 };
 int launch_lk_level(const LkLevelArgs &a, cudaStream_t stream, unsigned long long *launches);
+int preload_lk_level(int win); // loads the window's kernels now instead of at their first launch
+int preload_pyramid();
 
 // ---- pyramid (pyramid.cu) ------------------------------------------------------------------
 int launch_pyr_down(const uint8_t *src, size_t src_pitch, size_t src_stride, int sw, int sh, uint8_t *dst,

@@ -96,6 +96,13 @@ pyr_down_interleaved_kernel(const uint8_t *__restrict__ src, size_t src_pitch, i
     dst[(size_t)y * dst_pitch + xb] = (uint8_t)(acc >> 4);
 }
 
+int preload_pyramid()
+{
+    cudaFuncAttributes fa;
+    OFB_CUDA_TRY(cudaFuncGetAttributes(&fa, pyr_down_planar_kernel));
+    return OFB_OK;
+}
+
 int launch_pyr_down_strip(const uint8_t *src, size_t src_pitch, int sw, int src_rows, int src_y_off, uint8_t *dst,
                           size_t dst_pitch, int dst_y0, int dst_y1, cudaStream_t stream, unsigned long long *launches)
 {

@@ -9,6 +9,12 @@
 // pair of L levels costs L exchanges: one for the images, L-1 for the cumulative flow.  The Python StripRunner runs
 // the 2L-1-exchange form of the schedule through torch and is bound by ~100 us of host work per exchange.
 //
+// Second transport, peer memory (ofb_strips_peer_*): every rank keeps the buffers its neighbours write into -- the
+// level-0 image rows and the coarser cumulative-flow rows -- in ONE device allocation (the arena) whose CUDA IPC
+// handle the application all-gathers once.  An exchange is then a copy kernel of the SENDER that stores the halo rows
+// straight into the receiver's arena over NVLink and raises an epoch flag there, and a one-block wait kernel on the
+// receiver's stream; no NCCL call, no host work beyond two launches (~5 us instead of ~30 us per exchange).
+//
 // NCCL is not a link-time dependency of the library: libnccl.so.2 is opened on first use (inside a torch process
 // that is the copy torch already loaded), and every symbol is resolved with dlsym.
 #include "ofb_common.cuh"
@@ -128,6 +134,128 @@ struct StripPlan {
         return v;
     }
 };
+
+// ---- peer-memory transport ------------------------------------------------------------------------------------
+// Arena of one rank: [prev level 0][next level 0][cum_in level 0 .. L-2][flags].  Every rank can compute every other
+// rank's layout from the plan, so a peer address is (peer arena base) + (offset computed here).
+constexpr int PEER_MAX_SEG = 8;   // copy segments per exchange (prev + next rows per destination)
+constexpr int PEER_MAX_DST = 4;   // ranks one exchange sends to / receives from
+struct ArenaLayout {
+    size_t prev0, next0, cum_in[OFB_MAX_LEVELS], flags, bytes;
+    // flags (unsigned): arrive[x * world + src] = epoch of the last exchange x that src completed into this arena;
+    //                   done[src] at L * world + src = last epoch rank src finished reading what this rank pushed;
+    //                   counter[x] at (L + 1) * world + x: blocks of this rank's push kernel that have finished (local).
+};
+static ArenaLayout arena_layout(const StripPlan &pl, int rank)
+{
+    ArenaLayout a{};
+    const std::vector<LevelStrip> v = pl.strips(rank);
+    size_t off = 0;
+    auto take = [&](size_t n) {
+        const size_t o = off;
+        off += (n + 255) / 256 * 256;
+        return o;
+    };
+    const size_t pitch0 = ((size_t)v[0].w + 63) / 64 * 64;
+    a.prev0 = take(pitch0 * (v[0].eb1 - v[0].eb0));
+    a.next0 = take(pitch0 * (v[0].eb1 - v[0].eb0));
+    for (int k = 0; k < pl.levels; k++) a.cum_in[k] = take((size_t)(v[k].w >> 1) * std::max(v[k].cy1 - v[k].cy0, 1) * 8);
+    a.flags = take(((size_t)(pl.levels + 1) * pl.world + pl.levels) * sizeof(unsigned));
+    a.bytes = off;
+    return a;
+}
+
+struct PeerSeg {
+    const void *src;
+    void *dst; // inside a peer's arena
+    size_t bytes; // multiple of 8
+};
+struct PeerPushArgs {
+    PeerSeg seg[PEER_MAX_SEG];
+    int nseg, ndst;
+    unsigned *arrive[PEER_MAX_DST];           // arrive[x * world + me] in the arena of each destination
+    const unsigned *done_local[PEER_MAX_DST]; // done[dst] in MY arena: dst has finished with what I pushed last pair
+    unsigned *counter;                        // counter[x] in my arena
+    unsigned epoch;
+    int *err;
+};
+struct PeerWaitArgs {
+    const unsigned *flag[PEER_MAX_DST]; // arrive[x * world + src] in my arena
+    int n;
+    unsigned epoch;
+    int *err;
+};
+struct PeerDoneArgs {
+    unsigned *flag[2 * PEER_MAX_DST]; // done[me] in the arena of every rank that pushes to me
+    int n;
+    unsigned epoch;
+};
+constexpr unsigned long long PEER_TIMEOUT_NS = 4000000000ull; // a peer that never shows up: flag the pair, do not hang
+
+__device__ __forceinline__ unsigned long long peer_now()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ unsigned peer_ld(const unsigned *p)
+{
+    unsigned v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+// true when *p has reached `epoch` (wrap-safe), false after PEER_TIMEOUT_NS
+__device__ bool peer_spin(const unsigned *p, unsigned epoch)
+{
+    const unsigned long long t0 = peer_now();
+    while ((int)(peer_ld(p) - epoch) < 0) {
+        if (peer_now() - t0 > PEER_TIMEOUT_NS) return false;
+        __nanosleep(100);
+    }
+    return true;
+}
+
+// Sender side of one exchange: wait until every destination has finished with last pair's rows, store the segments into
+// the destinations' arenas (peer stores over NVLink), and -- last block out -- raise the epoch flag in each of them.
+__global__ void __launch_bounds__(256) peer_push_kernel(const __grid_constant__ PeerPushArgs a)
+{
+    if (threadIdx.x < a.ndst && !peer_spin(a.done_local[threadIdx.x], a.epoch - 1u)) atomicOr(a.err, 2);
+    __syncthreads();
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nt = (size_t)gridDim.x * blockDim.x;
+    for (int s = 0; s < a.nseg; s++) {
+        const PeerSeg g = a.seg[s];
+        if (((reinterpret_cast<uintptr_t>(g.src) | reinterpret_cast<uintptr_t>(g.dst) | g.bytes) & 15) == 0) {
+            const uint4 *src = static_cast<const uint4 *>(g.src);
+            uint4 *dst = static_cast<uint4 *>(g.dst);
+            for (size_t i = t; i < g.bytes / 16; i += nt) dst[i] = src[i];
+        } else {
+            const uint2 *src = static_cast<const uint2 *>(g.src);
+            uint2 *dst = static_cast<uint2 *>(g.dst);
+            for (size_t i = t; i < g.bytes / 8; i += nt) dst[i] = src[i];
+        }
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned arrived = atomicAdd(a.counter, 1u);
+        if (arrived == gridDim.x - 1) {
+            *a.counter = 0u;
+            __threadfence_system();
+            for (int d = 0; d < a.ndst; d++) asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(a.arrive[d]), "r"(a.epoch) : "memory");
+        }
+    }
+}
+// Receiver side: one thread per source spins on its epoch flag.
+__global__ void peer_wait_kernel(const __grid_constant__ PeerWaitArgs a)
+{
+    if (threadIdx.x < a.n && !peer_spin(a.flag[threadIdx.x], a.epoch)) atomicOr(a.err, 2);
+    __threadfence_system();
+}
+// End of a pair: tell every rank that pushes to me that its rows have been used.
+__global__ void peer_done_kernel(const __grid_constant__ PeerDoneArgs a)
+{
+    if (threadIdx.x < a.n) asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(a.flag[threadIdx.x]), "r"(a.epoch) : "memory");
+}
 } // namespace ofb
 
 using namespace ofb;
@@ -145,6 +273,14 @@ struct ofb_strips {
     std::vector<float *> flow, cum, cum_in;    // flow / cum: buffer rows (origin eb0); cum_in[k]: rows [cy0, cy1) of cum_{k+1}
     int *overflow = nullptr;
     std::vector<void *> allocs;
+    // peer-memory transport
+    uint8_t *arena = nullptr;               // my arena (one cudaMalloc: prev[0], next[0], cum_in[], flags live in it)
+    ArenaLayout lay;
+    std::vector<uint8_t *> peer_arena;      // base of every rank's arena in this process's address space (nullptr: not mapped)
+    std::vector<ArenaLayout> peer_lay;
+    std::vector<void *> ipc_opened;
+    bool peers_connected = false;
+    unsigned epoch = 0;
 };
 
 namespace {
@@ -161,6 +297,74 @@ inline bool overlap(int own0, int own1, int b0, int b1, int *lo, int *hi)
     *lo = std::max(own0, b0);
     *hi = std::min(own1, b1);
     return *lo < *hi;
+}
+
+// ---- peer-memory transport: one exchange ------------------------------------------------------------------------------
+struct PeerSend {
+    int peer;
+    const void *src;
+    size_t dst_off; // in the peer's arena
+    size_t bytes;
+};
+inline unsigned *flag_ptr(uint8_t *arena, const ArenaLayout &lay, size_t index)
+{
+    return reinterpret_cast<unsigned *>(arena + lay.flags) + index;
+}
+// Exchange x of the pair with epoch `epoch`: push `sends`, then wait for the ranks in `sources`.
+int peer_exchange(ofb_strips *st, int x, unsigned epoch, const std::vector<PeerSend> &sends, const std::vector<int> &sources,
+                  cudaStream_t q, unsigned long long *launches)
+{
+    const int world = st->plan.world, L = st->plan.levels, me = st->rank;
+    if (!sends.empty()) {
+        PeerPushArgs a{};
+        size_t total = 0;
+        for (const PeerSend &sd : sends) {
+            if (a.nseg == PEER_MAX_SEG || !st->peer_arena[sd.peer]) {
+                set_error("strips: exchange %d has too many segments or an unmapped peer %d (strips thinner than the halo?)", x, sd.peer);
+                return OFB_ERR_UNSUPPORTED;
+            }
+            a.seg[a.nseg++] = PeerSeg{sd.src, st->peer_arena[sd.peer] + sd.dst_off, sd.bytes};
+            total += sd.bytes;
+            bool seen = false;
+            for (int d = 0; d < a.ndst; d++) seen |= a.arrive[d] == flag_ptr(st->peer_arena[sd.peer], st->peer_lay[sd.peer], (size_t)x * world + me);
+            if (!seen) {
+                if (a.ndst == PEER_MAX_DST) {
+                    set_error("strips: exchange %d sends to more than %d ranks", x, PEER_MAX_DST);
+                    return OFB_ERR_UNSUPPORTED;
+                }
+                a.arrive[a.ndst] = flag_ptr(st->peer_arena[sd.peer], st->peer_lay[sd.peer], (size_t)x * world + me);
+                a.done_local[a.ndst] = flag_ptr(st->arena, st->lay, (size_t)L * world + sd.peer);
+                a.ndst++;
+            }
+        }
+        a.counter = flag_ptr(st->arena, st->lay, (size_t)(L + 1) * world + x);
+        a.epoch = epoch;
+        a.err = st->overflow;
+        const unsigned blocks = (unsigned)std::min<size_t>(64, std::max<size_t>(1, total / (256 * 64)));
+        peer_push_kernel<<<blocks, 256, 0, q>>>(a);
+        OFB_CUDA_TRY(cudaGetLastError());
+        if (launches) ++*launches;
+    }
+    if (!sources.empty()) {
+        PeerWaitArgs w{};
+        for (int src : sources) {
+            if (w.n == PEER_MAX_DST) {
+                set_error("strips: exchange %d receives from more than %d ranks", x, PEER_MAX_DST);
+                return OFB_ERR_UNSUPPORTED;
+            }
+            w.flag[w.n++] = flag_ptr(st->arena, st->lay, (size_t)x * world + src);
+        }
+        w.epoch = epoch;
+        w.err = st->overflow;
+        peer_wait_kernel<<<1, 32, 0, q>>>(w);
+        OFB_CUDA_TRY(cudaGetLastError());
+        if (launches) ++*launches;
+    }
+    return OFB_OK;
+}
+void add_unique(std::vector<int> &v, int x)
+{
+    if (std::find(v.begin(), v.end(), x) == v.end()) v.push_back(x);
 }
 } // namespace
 
@@ -200,10 +404,6 @@ int ofb_strips_create(ofb_ctx *ctx, int w, int h, int levels, int win, int warp_
         set_error("coarsest level has %d rows, cannot cut it into %d strips", hc, world);
         return OFB_ERR_INVALID;
     }
-    if (world > 1 && !nccl_id128) {
-        set_error("strips_create: a NCCL unique id is required for world > 1");
-        return OFB_ERR_INVALID;
-    }
     OFB_CUDA_TRY(cudaSetDevice(ctx_device(ctx)));
     ofb_strips *st = new ofb_strips;
     st->ctx = ctx;
@@ -220,29 +420,40 @@ int ofb_strips_create(ofb_ctx *ctx, int w, int h, int levels, int win, int warp_
     int rc = OFB_OK;
     st->s = pl.strips(rank);
     for (int peer = 0; peer < world; peer++) st->peer0.push_back(pl.strips(peer)[0]);
+    // what neighbours write into (level-0 image rows, coarser cumulative-flow rows, flags): one allocation, the arena
+    st->lay = arena_layout(pl, rank);
+    {
+        void *p = nullptr;
+        rc = dev_alloc(st, &p, st->lay.bytes);
+        st->arena = static_cast<uint8_t *>(p);
+    }
     for (int k = 0; k < levels && rc == OFB_OK; k++) {
         const LevelStrip s = st->s[k];
         const size_t pitch = ((size_t)s.w + 63) / 64 * 64;
         st->pitch.push_back(pitch);
         void *p = nullptr;
         const int rows = s.eb1 - s.eb0;
-        if ((rc = dev_alloc(st, &p, pitch * rows))) break;
-        st->prev.push_back(static_cast<uint8_t *>(p));
-        if ((rc = dev_alloc(st, &p, pitch * rows))) break;
-        st->next.push_back(static_cast<uint8_t *>(p));
+        if (k == 0) {
+            st->prev.push_back(st->arena + st->lay.prev0);
+            st->next.push_back(st->arena + st->lay.next0);
+        } else {
+            if ((rc = dev_alloc(st, &p, pitch * rows))) break;
+            st->prev.push_back(static_cast<uint8_t *>(p));
+            if ((rc = dev_alloc(st, &p, pitch * rows))) break;
+            st->next.push_back(static_cast<uint8_t *>(p));
+        }
         if ((rc = dev_alloc(st, &p, (size_t)s.w * rows * 8))) break;
         st->flow.push_back(static_cast<float *>(p));
         if ((rc = dev_alloc(st, &p, (size_t)s.w * rows * 8))) break;
         st->cum.push_back(static_cast<float *>(p));
-        if ((rc = dev_alloc(st, &p, (size_t)(s.w >> 1) * std::max(s.cy1 - s.cy0, 1) * 8))) break;
-        st->cum_in.push_back(static_cast<float *>(p));
+        st->cum_in.push_back(reinterpret_cast<float *>(st->arena + st->lay.cum_in[k]));
     }
     if (rc == OFB_OK) {
         void *p = nullptr;
         rc = dev_alloc(st, &p, sizeof(int));
         st->overflow = static_cast<int *>(p);
     }
-    if (rc == OFB_OK && world > 1) {
+    if (rc == OFB_OK && world > 1 && nccl_id128) {
         NcclApi *n = nccl();
         if (!n) {
             set_error("libnccl.so.2 could not be loaded");
@@ -257,6 +468,22 @@ int ofb_strips_create(ofb_ctx *ctx, int w, int h, int levels, int win, int warp_
             }
         }
     }
+    // every kernel a pair launches is loaded now: a lazily loaded kernel may synchronise the context at its first
+    // launch, which must not happen behind a kernel that waits for a neighbour
+    if (rc == OFB_OK) rc = preload_lk_level(win);
+    if (rc == OFB_OK) rc = preload_pyramid();
+    if (rc == OFB_OK) {
+        cudaFuncAttributes fa;
+        if (cudaFuncGetAttributes(&fa, peer_push_kernel) != cudaSuccess || cudaFuncGetAttributes(&fa, peer_wait_kernel) != cudaSuccess ||
+            cudaFuncGetAttributes(&fa, peer_done_kernel) != cudaSuccess) {
+            set_error("strips_create: loading the exchange kernels failed");
+            rc = OFB_ERR_CUDA;
+        }
+    }
+    if (rc == OFB_OK && cudaDeviceSynchronize() != cudaSuccess) { // the zeroed flags must be in place before a peer can see the arena
+        set_error("strips_create: device synchronisation failed");
+        rc = OFB_ERR_CUDA;
+    }
     if (rc != OFB_OK) {
         for (void *p : st->allocs) cudaFree(p);
         delete st;
@@ -266,10 +493,119 @@ int ofb_strips_create(ofb_ctx *ctx, int w, int h, int levels, int win, int warp_
     return OFB_OK;
 }
 
+// ---- peer-memory transport: set-up -------------------------------------------------------------------------------
+// The 128-byte blob a rank publishes: its arena's CUDA IPC handle and the arena's offset inside the allocation the
+// handle stands for (small cudaMalloc blocks share one).
+int ofb_strips_peer_handle(ofb_strips *st, void *blob128)
+{
+    if (!st || !blob128) {
+        set_error("strips_peer_handle: bad arguments");
+        return OFB_ERR_INVALID;
+    }
+    OFB_CUDA_TRY(cudaSetDevice(ctx_device(st->ctx)));
+    memset(blob128, 0, 128);
+    cudaIpcMemHandle_t h;
+    OFB_CUDA_TRY(cudaIpcGetMemHandle(&h, st->arena));
+    static_assert(sizeof h == 64, "CUDA IPC handle size");
+    memcpy(blob128, &h, sizeof h);
+    unsigned long long off = 0;
+    {
+        typedef int (*GetRange)(unsigned long long *, size_t *, unsigned long long);
+        void *sym = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        unsigned long long base = 0;
+        size_t size = 0;
+        if (cudaGetDriverEntryPoint("cuMemGetAddressRange", &sym, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess && sym &&
+            reinterpret_cast<GetRange>(sym)(&base, &size, (unsigned long long)reinterpret_cast<uintptr_t>(st->arena)) == 0)
+            off = (unsigned long long)reinterpret_cast<uintptr_t>(st->arena) - base;
+        else {
+            set_error("strips_peer_handle: cuMemGetAddressRange failed");
+            return OFB_ERR_CUDA;
+        }
+    }
+    memcpy(static_cast<char *>(blob128) + 64, &off, sizeof off);
+    return OFB_OK;
+}
+
+int ofb_strips_peer_arena(ofb_strips *st, void **arena)
+{
+    if (!st || !arena) {
+        set_error("strips_peer_arena: bad arguments");
+        return OFB_ERR_INVALID;
+    }
+    *arena = st->arena;
+    return OFB_OK;
+}
+
+namespace {
+// ranks whose buffers I write into, or that write into mine, at any exchange
+bool is_neighbour(const ofb_strips *st, int peer)
+{
+    const StripPlan &pl = st->plan;
+    int lo, hi;
+    const LevelStrip &s = st->s[0], &ps = st->peer0[peer];
+    if (overlap(s.y0, s.y1, ps.eb0, ps.eb1, &lo, &hi) || overlap(ps.y0, ps.y1, s.eb0, s.eb1, &lo, &hi)) return true;
+    for (int k = 0; k + 1 < pl.levels; k++) {
+        const LevelStrip up = st->s[k + 1], sk = st->s[k], pk = pl.level(k, peer), pu = pl.level(k + 1, peer);
+        if (overlap(up.y0, up.y1, pk.cy0, pk.cy1, &lo, &hi) || overlap(pu.y0, pu.y1, sk.cy0, sk.cy1, &lo, &hi)) return true;
+    }
+    return false;
+}
+int finish_connect(ofb_strips *st)
+{
+    st->peer_lay.clear();
+    for (int peer = 0; peer < st->plan.world; peer++) st->peer_lay.push_back(arena_layout(st->plan, peer));
+    st->peers_connected = true;
+    return OFB_OK;
+}
+} // namespace
+
+// blobs: world x 128 bytes, rank r's ofb_strips_peer_handle blob at 128 * r (an all-gather by the application).
+int ofb_strips_peer_connect(ofb_strips *st, const void *blobs)
+{
+    if (!st || !blobs) {
+        set_error("strips_peer_connect: bad arguments");
+        return OFB_ERR_INVALID;
+    }
+    OFB_CUDA_TRY(cudaSetDevice(ctx_device(st->ctx)));
+    const int world = st->plan.world;
+    st->peer_arena.assign(world, nullptr);
+    st->peer_arena[st->rank] = st->arena;
+    for (int peer = 0; peer < world; peer++) {
+        if (peer == st->rank || !is_neighbour(st, peer)) continue;
+        cudaIpcMemHandle_t h;
+        unsigned long long off = 0;
+        memcpy(&h, static_cast<const char *>(blobs) + 128 * (size_t)peer, sizeof h);
+        memcpy(&off, static_cast<const char *>(blobs) + 128 * (size_t)peer + 64, sizeof off);
+        void *base = nullptr;
+        OFB_CUDA_TRY(cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess));
+        st->ipc_opened.push_back(base);
+        st->peer_arena[peer] = static_cast<uint8_t *>(base) + off;
+    }
+    return finish_connect(st);
+}
+
+// Same, for ranks that live in ONE process (tests; a single-process multi-GPU host with peer access enabled by the
+// caller): arenas[r] = ofb_strips_peer_arena of rank r.
+int ofb_strips_peer_connect_local(ofb_strips *st, void *const *arenas)
+{
+    if (!st || !arenas) {
+        set_error("strips_peer_connect_local: bad arguments");
+        return OFB_ERR_INVALID;
+    }
+    st->peer_arena.assign(st->plan.world, nullptr);
+    for (int peer = 0; peer < st->plan.world; peer++) st->peer_arena[peer] = static_cast<uint8_t *>(arenas[peer]);
+    st->peer_arena[st->rank] = st->arena;
+    return finish_connect(st);
+}
+
 int ofb_strips_destroy(ofb_strips *st)
 {
     if (!st) return OFB_OK;
     cudaSetDevice(ctx_device(st->ctx));
+    cudaDeviceSynchronize();
+    for (void *p : st->ipc_opened) cudaIpcCloseMemHandle(p);
     if (st->comm && nccl()) nccl()->CommDestroy(st->comm);
     for (void *p : st->allocs) cudaFree(p);
     delete st;
@@ -312,9 +648,16 @@ int ofb_strips_run_device(ofb_strips *st, const uint8_t *prev_own_d, const uint8
     OFB_CUDA_TRY(cudaSetDevice(ctx_device(st->ctx)));
     cudaStream_t q = static_cast<cudaStream_t>(stream);
     const StripPlan &pl = st->plan;
-    NcclApi *n = pl.world > 1 ? nccl() : nullptr;
+    const bool peer_mode = pl.world > 1 && !st->comm;
+    if (peer_mode && !st->peers_connected) {
+        set_error("strips_run: no transport (create with a NCCL id, or call ofb_strips_peer_connect first)");
+        return OFB_ERR_INVALID;
+    }
+    NcclApi *n = pl.world > 1 && !peer_mode ? nccl() : nullptr;
     unsigned long long *launches = ctx_launch_counter(st->ctx);
     const int L = pl.levels, me = st->rank;
+    const unsigned epoch = ++st->epoch;
+    std::vector<int> all_sources; // every rank that pushes to me during the pair
     if (pitch < (size_t)pl.W) {
         set_error("strips_run: pitch %zu smaller than the width %d", pitch, pl.W);
         return OFB_ERR_INVALID;
@@ -347,6 +690,28 @@ int ofb_strips_run_device(ofb_strips *st, const uint8_t *prev_own_d, const uint8
             }
         }
         OFB_NCCL_TRY(n->GroupEnd());
+    }
+    if (peer_mode) {
+        const LevelStrip &s = st->s[0];
+        const size_t P = st->pitch[0];
+        std::vector<PeerSend> sends;
+        std::vector<int> sources;
+        for (int peer = 0; peer < pl.world; peer++) {
+            if (peer == me) continue;
+            const LevelStrip &ps = st->peer0[peer];
+            int lo, hi;
+            if (overlap(s.y0, s.y1, ps.eb0, ps.eb1, &lo, &hi)) { // my rows the peer's buffer holds
+                const ArenaLayout &pa = st->peer_lay[peer];
+                sends.push_back({peer, st->prev[0] + (size_t)(lo - s.eb0) * P, pa.prev0 + (size_t)(lo - ps.eb0) * P, (size_t)(hi - lo) * P});
+                sends.push_back({peer, st->next[0] + (size_t)(lo - s.eb0) * P, pa.next0 + (size_t)(lo - ps.eb0) * P, (size_t)(hi - lo) * P});
+            }
+            if (overlap(ps.y0, ps.y1, s.eb0, s.eb1, &lo, &hi)) { // the peer's rows my buffer holds
+                sources.push_back(peer);
+                add_unique(all_sources, peer);
+            }
+        }
+        int rc = peer_exchange(st, 0, epoch, sends, sources, q, launches);
+        if (rc) return rc;
     }
     // pyramid: every buffer row of level k+1 from the buffer rows of level k (halo rows are built locally)
     for (int k = 0; k + 1 < L; k++) {
@@ -381,6 +746,23 @@ int ofb_strips_run_device(ofb_strips *st, const uint8_t *prev_own_d, const uint8
                 }
                 OFB_NCCL_TRY(n->GroupEnd());
             }
+            if (peer_mode) {
+                std::vector<PeerSend> sends;
+                std::vector<int> sources;
+                for (int peer = 0; peer < pl.world; peer++) {
+                    if (peer == me) continue;
+                    const LevelStrip pk = pl.level(k, peer), pu = pl.level(k + 1, peer);
+                    if (overlap(up.y0, up.y1, pk.cy0, pk.cy1, &lo, &hi)) // my cum rows the peer needs
+                        sends.push_back({peer, src + (size_t)(lo - up.eb0) * rowf, st->peer_lay[peer].cum_in[k] + (size_t)(lo - pk.cy0) * rowf * 4,
+                                         (size_t)(hi - lo) * rowf * 4});
+                    if (overlap(pu.y0, pu.y1, s.cy0, s.cy1, &lo, &hi)) { // the peer's cum rows I need
+                        sources.push_back(peer);
+                        add_unique(all_sources, peer);
+                    }
+                }
+                int rc = peer_exchange(st, L - 1 - k, epoch, sends, sources, q, launches); // exchanges 1 .. L-1
+                if (rc) return rc;
+            }
         }
         LkLevelArgs a{};
         a.prev = st->prev[k];
@@ -411,6 +793,20 @@ int ofb_strips_run_device(ofb_strips *st, const uint8_t *prev_own_d, const uint8
         a.sm_count = ctx_sm_count(st->ctx);
         int rc = launch_lk_level(a, q, launches);
         if (rc) return rc;
+    }
+    if (peer_mode && !all_sources.empty()) { // the rows my neighbours pushed have been used: they may push the next pair's
+        PeerDoneArgs d{};
+        for (int src : all_sources) {
+            if (d.n == 2 * PEER_MAX_DST) {
+                set_error("strips: more than %d ranks push to this one", 2 * PEER_MAX_DST);
+                return OFB_ERR_UNSUPPORTED;
+            }
+            d.flag[d.n++] = flag_ptr(st->peer_arena[src], st->peer_lay[src], (size_t)L * pl.world + me);
+        }
+        d.epoch = epoch;
+        peer_done_kernel<<<1, 32, 0, q>>>(d);
+        OFB_CUDA_TRY(cudaGetLastError());
+        if (launches) ++*launches;
     }
     return OFB_OK;
 }

@@ -376,21 +376,26 @@ class StripRunner:
 
 class NativeStrips:
     """The native row-strip runner (csrc/strips.cu): the same schedule as StripRunner, but a whole pair is enqueued
-    from C++ on one stream and the halo rows move by NCCL send/recv between the ranks' buffers.  `torch.distributed`
-    is used once, to hand rank 0's NCCL unique id to the other ranks."""
+    from C++ on one stream.  transport "nccl": the halo rows move by NCCL send/recv between the ranks' buffers;
+    "peer": by the sender's copy kernel straight into the receiver's memory over NVLink (CUDA IPC), epoch flags instead
+    of a collective; "local": peer memory between ranks living in this process (connect_local, tests).
+    `torch.distributed` is used once, to hand round the NCCL unique id or the IPC handles."""
 
     def __init__(self, ctx, w: int, h: int, levels: int, win: int, world: int, rank: int, device, warp_mode: int = WARP_BILINEAR,
-                 flow_scale: float = 1.0, reach: int = 16):
+                 flow_scale: float = 1.0, reach: int = 16, transport: str = "nccl"):
         import ctypes as C
 
         import torch
 
         from . import _lib as L
 
+        if transport not in ("nccl", "peer", "local"):
+            raise ValueError(f"unknown strip transport {transport!r}")
         self.torch, self.C, self.L, self.lib, self.ctx = torch, C, L, L.load(), ctx
-        self.w, self.h, self.levels, self.dev = w, h, levels, device
+        self.w, self.h, self.levels, self.dev, self.world, self.rank = w, h, levels, device, world, rank
         idbuf = torch.zeros(128, dtype=torch.uint8)
-        if world > 1:
+        use_nccl = world > 1 and transport == "nccl"
+        if use_nccl:
             import torch.distributed as dist
 
             if rank == 0:
@@ -402,8 +407,33 @@ class NativeStrips:
         raw = (C.c_ubyte * 128)(*idbuf.cpu().tolist())
         hnd = C.c_void_p()
         L.check(self.lib.ofb_strips_create(ctx._h, w, h, levels, win, warp_mode, C.c_float(flow_scale), world, rank, reach,
-                                           C.cast(raw, C.c_void_p) if world > 1 else None, C.byref(hnd)))
+                                           C.cast(raw, C.c_void_p) if use_nccl else None, C.byref(hnd)))
         self._h = hnd
+        if world > 1 and transport == "peer":
+            import torch.distributed as dist
+
+            blob = (C.c_ubyte * 128)()
+            L.check(self.lib.ofb_strips_peer_handle(self._h, C.cast(blob, C.c_void_p)))
+            mine = torch.tensor(list(blob), dtype=torch.uint8, device=device)
+            every = torch.empty(world * 128, dtype=torch.uint8, device=device)
+            dist.all_gather_into_tensor(every, mine)
+            blobs = (C.c_ubyte * (world * 128))(*every.cpu().tolist())
+            L.check(self.lib.ofb_strips_peer_connect(self._h, C.cast(blobs, C.c_void_p)))
+            dist.barrier()  # nobody pushes before everybody has mapped its neighbours
+
+    def arena(self) -> int:
+        p = self.C.c_void_p()
+        self.L.check(self.lib.ofb_strips_peer_arena(self._h, self.C.byref(p)))
+        return p.value
+
+    @staticmethod
+    def connect_local(ranks) -> None:
+        """Peer-memory transport between NativeStrips objects of ONE process (ranks[r] is rank r)."""
+        import ctypes as C
+
+        arenas = (C.c_void_p * len(ranks))(*[r.arena() for r in ranks])
+        for r in ranks:
+            r.L.check(r.lib.ofb_strips_peer_connect_local(r._h, arenas))
 
     def own_rows(self, level: int = 0):
         y0, y1 = self.C.c_int(), self.C.c_int()
@@ -418,7 +448,9 @@ class NativeStrips:
     def check(self, stream: int = 0) -> None:
         v = self.C.c_int()
         self.L.check(self.lib.ofb_strips_check(self._h, self.C.c_void_p(stream), self.C.byref(v)))
-        if v.value:
+        if v.value & 2:
+            raise RuntimeError("a neighbour's halo rows did not arrive (peer-memory transport timed out)")
+        if v.value & 1:
             raise RuntimeError("a warp sample reached past the exchanged halo rows: raise `reach`")
 
     def own_flow(self, level: int, total: bool = False):

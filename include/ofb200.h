@@ -200,8 +200,18 @@ int ofb_stream_destroy(ofb_stream *s);
  * the halo rows move by NCCL send/recv between the ranks' buffers (libnccl.so.2 is opened on first use; it is not
  * a link-time dependency).  The result is bit-identical to the whole-frame result unless ofb_strips_check reports
  * that a warp sample reached past the exchanged rows (`reach`, in rows of the level being warped).
+ * Two transports for the halo rows:
+ *   NCCL send/recv   : ofb_strips_create with rank 0's broadcast ofb_strips_nccl_unique_id;
+ *   peer memory      : ofb_strips_create with nccl_id128 = NULL, then every rank publishes ofb_strips_peer_handle
+ *                      (128 bytes: a CUDA IPC handle of the one allocation its neighbours write into), the
+ *                      application all-gathers the blobs and hands them to ofb_strips_peer_connect.  An exchange is
+ *                      then a copy kernel of the sender that stores the rows into the receiver's memory over NVLink
+ *                      and raises an epoch flag there, plus a one-block wait kernel on the receiver's stream.
+ *                      ofb_strips_peer_connect_local does the same for ranks living in one process.
  *   ofb_strips_nccl_unique_id : rank 0 makes the 128-byte id, the application broadcasts it (any transport)
- *   ofb_strips_create         : collective over all ranks (ncclCommInitRank)
+ *   ofb_strips_create         : collective over all ranks when a NCCL id is given (ncclCommInitRank)
+ *   ofb_strips_check          : synchronises; *overflow bit 0 = a warp sample reached past the halo rows, bit 1 = a
+ *                               neighbour's rows did not arrive within 4 s (peer-memory transport)
  *   ofb_strips_run_device     : prev_own_d / next_own_d = rows [y0, y1) of level 0 (ofb_strips_own_rows), planar u8
  *   ofb_strips_result         : device pointers to the own rows of the residual flow / cumulative flow of a level */
 typedef struct ofb_strips ofb_strips;
@@ -213,6 +223,10 @@ int ofb_strips_run_device(ofb_strips *s, const uint8_t *prev_own_d, const uint8_
 int ofb_strips_result(const ofb_strips *s, int level, float **flow_own_d, float **total_own_d);
 int ofb_strips_check(ofb_strips *s, void *stream, int *overflow);
 int ofb_strips_destroy(ofb_strips *s);
+int ofb_strips_peer_handle(ofb_strips *s, void *blob128);
+int ofb_strips_peer_connect(ofb_strips *s, const void *blobs_world_x_128);
+int ofb_strips_peer_arena(ofb_strips *s, void **arena_d);
+int ofb_strips_peer_connect_local(ofb_strips *s, void *const *arenas_d);
 
 /* ---- debug derivative views: showTest (main.cu:19-92) without the windows ------------------------------------------
  * ofb_conv_3ch_1ch_u8_u8_host replaces gpu::conv_3ch_1ch_tiled (OptFlowGpu.cuh; OptFlowGpu.cu:741-766, kernel

@@ -18,7 +18,7 @@ ap.add_argument("--w", type=int, default=7680); ap.add_argument("--h", type=int,
 ap.add_argument("--levels", type=int, default=4); ap.add_argument("--win", type=int, default=9)
 ap.add_argument("--reps", type=int, default=10); ap.add_argument("--reach", type=int, default=16)
 ap.add_argument("--check", action="store_true")
-ap.add_argument("--transport", default="gather", choices=["gather", "p2p"], help="halo exchange: one all-gather per exchange (graph-capturable) or grouped send/recv")
+ap.add_argument("--transport", default="gather", choices=["gather", "p2p", "nccl", "peer"], help="Python runner: one all-gather per exchange (gather) or grouped send/recv (p2p); --native: NCCL send/recv (nccl, default) or the sender's copy kernel into the receiver's memory over NVLink with epoch flags (peer)")
 ap.add_argument("--native", action="store_true", help="the native runner (csrc/strips.cu: C++ host side, NCCL send/recv between the ranks' buffers)")
 ap.add_argument("--graph", action="store_true", help="capture one pair in a CUDA graph and replay it (1 GPU: works, -8 %; with NCCL exchanges the capture hung on this stack, PyTorch 2.11 + NCCL 2.28: unresolved)")
 a = ap.parse_args()
@@ -36,14 +36,14 @@ class Solo(DistTransport):
 
 if world == 1:
     tp = type("T", (), {"exchange": lambda self, s, r: None})()
-elif a.transport == "gather":
+elif a.transport in ("gather", "nccl", "peer"):
     tp = GatherTransport(rank, world, dev)
 else:
     tp = Solo()
 rn = StripRunner(ctx, plan, rank, tp, dev, WARP_BILINEAR)
 s0 = rn.strips[0]
 pr, nr = prev[0, s0.y0:s0.y1, :a.w], nxt[0, s0.y0:s0.y1, :a.w]
-nat = NativeStrips(ctx, a.w, a.h, a.levels, a.win, world, rank, dev, WARP_BILINEAR, 1.0, a.reach) if a.native else None
+nat = NativeStrips(ctx, a.w, a.h, a.levels, a.win, world, rank, dev, WARP_BILINEAR, 1.0, a.reach, transport="peer" if a.transport == "peer" else "nccl") if a.native else None
 def one():
     if nat is not None:
         nat.run(prev[0, s0.y0:s0.y1], nxt[0, s0.y0:s0.y1], torch.cuda.current_stream(dev).cuda_stream)

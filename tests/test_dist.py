@@ -215,3 +215,46 @@ def test_native_strip_runner_world_one_equals_whole_frame(ctx, oracle, W, H, lev
             assert torch.equal(torch.isnan(ref), torch.isnan(got)) and torch.equal(ref[m], got[m]), f"level {k}"
     finally:
         ns.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("W,H,levels,win,world", [(640, 480, 3, 9, 2), (322, 406, 2, 5, 3), (1920, 1080, 4, 15, 4),
+                                                   (7680, 4320, 4, 9, 8)])
+def test_native_strips_peer_memory_transport_equals_whole_frame(ctx, oracle, W, H, levels, win, world):
+    """csrc/strips.cu with the peer-memory transport: `world` ranks live in this process on one GPU, each with its own
+    stream; the sender's copy kernel stores halo rows straight into the receiver's arena and raises an epoch flag, the
+    receiver's wait kernel spins on it.  Three pairs back to back (flags, epochs and the done handshake are re-used),
+    each bit for bit the whole-frame result.  Across processes the same kernels run on CUDA IPC mappings
+    (scripts/run_strips.py --native --transport peer under torchrun)."""
+    import torch
+
+    from cuda_optical_flow_2_b200 import WARP_BILINEAR, planar_to_device
+    from cuda_optical_flow_2_b200.dist import NativeStrips
+
+    dev = torch.device("cuda", 0)
+    ranks = [NativeStrips(ctx, W, H, levels, win, world, rk, dev, WARP_BILINEAR, 1.0, 16, transport="local") for rk in range(world)]
+    streams = [torch.cuda.Stream(dev) for _ in range(world)]
+    try:
+        NativeStrips.connect_local(ranks)
+        for trial, (dx, dy) in enumerate([(2.25, -1.5), (-3.0, 0.75), (0.5, 2.0)]):
+            prev = oracle.make_frame(W, H, 0, 0, 8, 900 + trial)
+            nxt = oracle.make_frame(W, H, dx, dy, 8, 900 + trial)
+            dp, dn = planar_to_device(prev[None]), planar_to_device(nxt[None])
+            whole = ctx.flow_pairs_device(dp, dn, W, levels, win, warp_mode=WARP_BILINEAR)
+            torch.cuda.synchronize()
+            for rk, (ns, st) in enumerate(zip(ranks, streams)):
+                y0, y1 = ns.own_rows(0)
+                ns.run(dp[0, y0:y1], dn[0, y0:y1], st.cuda_stream)
+            for ns, st in zip(ranks, streams):
+                ns.check(st.cuda_stream)
+            for ns in ranks:
+                for k in range(levels):
+                    y0, y1 = ns.own_rows(k)
+                    ref, got = whole[k][0, y0:y1], ns.own_flow(k)
+                    m = ~torch.isnan(ref)
+                    assert torch.equal(torch.isnan(ref), torch.isnan(got)) and torch.equal(ref[m], got[m]), \
+                        f"pair {trial} rank {ns.rank} level {k}"
+    finally:
+        torch.cuda.synchronize()
+        for ns in ranks:
+            ns.close()
