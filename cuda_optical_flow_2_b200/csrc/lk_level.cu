@@ -104,8 +104,10 @@ int launch_lk_level(const LkLevelArgs &a, cudaStream_t stream, unsigned long lon
         set_error("lk_level: unknown warp mode %d", a.warp_mode);
         return OFB_ERR_INVALID;
     }
-    if ((reinterpret_cast<uintptr_t>(a.flow_out) & 15) || (a.cum_out && (reinterpret_cast<uintptr_t>(a.cum_out) & 15))) {
-        set_error("lk_level: flow buffers must be 16-byte aligned");
+    // (the kernel picks 256-bit, 128-bit or scalar stores per row segment from the actual addresses; the cumulative
+    // flow of a row strip lands inside the next level's buffer at a row offset, which for odd widths is 8-byte aligned)
+    if ((reinterpret_cast<uintptr_t>(a.flow_out) & 15) || (a.cum_out && (reinterpret_cast<uintptr_t>(a.cum_out) & 7))) {
+        set_error("lk_level: the flow buffer must be 16-byte aligned, the cumulative flow 8-byte aligned");
         return OFB_ERR_INVALID;
     }
     switch (a.win) {

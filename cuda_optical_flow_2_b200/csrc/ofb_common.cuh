@@ -56,7 +56,8 @@ int launch_pyr_down(const uint8_t *src, size_t src_pitch, size_t src_stride, int
                     unsigned long long *launches);
 
 int launch_pyr_down_strip(const uint8_t *src, size_t src_pitch, int sw, int src_rows, int src_y_off, uint8_t *dst,
-                          size_t dst_pitch, int dst_y0, int dst_y1, cudaStream_t stream, unsigned long long *launches);
+                          size_t dst_pitch, int dst_y0, int dst_y1, cudaStream_t stream, unsigned long long *launches,
+                          int n_images = 1, size_t src_stride = 0, size_t dst_stride = 0);
 
 // ---- stage kernels + layout helpers (stages.cu) --------------------------------------------
 int launch_c3_to_planar(const uint8_t *src_c3, int w, int h, int n_images, uint8_t *dst, size_t dst_pitch,

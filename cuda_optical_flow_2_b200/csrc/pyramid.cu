@@ -104,7 +104,8 @@ int preload_pyramid()
 }
 
 int launch_pyr_down_strip(const uint8_t *src, size_t src_pitch, int sw, int src_rows, int src_y_off, uint8_t *dst,
-                          size_t dst_pitch, int dst_y0, int dst_y1, cudaStream_t stream, unsigned long long *launches)
+                          size_t dst_pitch, int dst_y0, int dst_y1, cudaStream_t stream, unsigned long long *launches,
+                          int n_images, size_t src_stride, size_t dst_stride)
 {
     const int dw = sw >> 1, dh = dst_y1 - dst_y0;
     // rows 2*y-1 .. 2*y+1 of every destination row must be in the source strip (or above the image)
@@ -123,9 +124,13 @@ int launch_pyr_down_strip(const uint8_t *src, size_t src_pitch, int sw, int src_
         return OFB_ERR_INVALID;
     }
     dim3 block(32, 8);
-    dim3 grid((unsigned)((dw + 255) / 256), (unsigned)((dh + 15) / 16), 1);
-    pyr_down_planar_kernel<<<grid, block, 0, stream>>>(src, src_pitch, 0, dw, dh, dst, dst_pitch, 0, src_y_off, dst_y0,
-                                                       src_rows);
+    if (n_images < 1 || (src_stride & 15) || (dst_stride & 3)) {
+        set_error("pyr_down_strip: bad image count / strides");
+        return OFB_ERR_INVALID;
+    }
+    dim3 grid((unsigned)((dw + 255) / 256), (unsigned)((dh + 15) / 16), (unsigned)n_images);
+    pyr_down_planar_kernel<<<grid, block, 0, stream>>>(src, src_pitch, src_stride, dw, dh, dst, dst_pitch, dst_stride, src_y_off,
+                                                       dst_y0, src_rows);
     OFB_CUDA_TRY(cudaGetLastError());
     if (launches) ++*launches;
     return OFB_OK;

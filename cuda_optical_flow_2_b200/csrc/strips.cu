@@ -271,6 +271,10 @@ struct ofb_strips {
     std::vector<size_t> pitch;                 // image pitch per level
     std::vector<uint8_t *> prev, next;         // [eb0, eb1) rows
     std::vector<float *> flow, cum, cum_in;    // flow / cum: buffer rows (origin eb0); cum_in[k]: rows [cy0, cy1) of cum_{k+1}
+    std::vector<size_t> img_stride;            // next[k] - prev[k]: both frames of a level are one batch of two images
+    std::vector<float *> cum_dst;              // where level k's kernel writes its cumulative flow (buffer-row indexing like
+                                               // flow[k]): straight into cum_in[k-1], whose rows [cy0, cy1) contain the own rows
+    int want_total = 1;                        // level 0 also writes its cumulative flow (the total flow of the pair)
     int *overflow = nullptr;
     std::vector<void *> allocs;
     // peer-memory transport
@@ -436,17 +440,36 @@ int ofb_strips_create(ofb_ctx *ctx, int w, int h, int levels, int win, int warp_
         if (k == 0) {
             st->prev.push_back(st->arena + st->lay.prev0);
             st->next.push_back(st->arena + st->lay.next0);
-        } else {
-            if ((rc = dev_alloc(st, &p, pitch * rows))) break;
+            st->img_stride.push_back(st->lay.next0 - st->lay.prev0);
+        } else { // one block: the pyramid step handles prev and next as a batch of two
+            const size_t stride = (pitch * rows + 255) / 256 * 256;
+            if ((rc = dev_alloc(st, &p, 2 * stride))) break;
             st->prev.push_back(static_cast<uint8_t *>(p));
-            if ((rc = dev_alloc(st, &p, pitch * rows))) break;
-            st->next.push_back(static_cast<uint8_t *>(p));
+            st->next.push_back(static_cast<uint8_t *>(p) + stride);
+            st->img_stride.push_back(stride);
         }
         if ((rc = dev_alloc(st, &p, (size_t)s.w * rows * 8))) break;
         st->flow.push_back(static_cast<float *>(p));
-        if ((rc = dev_alloc(st, &p, (size_t)s.w * rows * 8))) break;
+        // the cumulative flow of level 0 (the total flow) has its own buffer; levels >= 1 write theirs straight into the
+        // buffer the next finer level reads (below), whose other rows the neighbours fill
+        p = nullptr;
+        if (k == 0 && (rc = dev_alloc(st, &p, (size_t)s.w * rows * 8))) break;
         st->cum.push_back(static_cast<float *>(p));
         st->cum_in.push_back(reinterpret_cast<float *>(st->arena + st->lay.cum_in[k]));
+    }
+    for (int k = 0; k < levels && rc == OFB_OK; k++) {
+        // buffer row b of level k is global row eb0 + b; row g of cum_in[k-1] sits at (g - cy0) * w
+        float *dst = st->cum[k];
+        if (k > 0) {
+            const LevelStrip &s = st->s[k], &fine = st->s[k - 1];
+            dst = st->cum_in[k - 1] + ((ptrdiff_t)s.eb0 - fine.cy0) * (ptrdiff_t)s.w * 2;
+            if (s.y0 < fine.cy0 || s.y1 > fine.cy1) {
+                set_error("strips_create: level %d own rows [%d,%d) outside the finer level's coarse window [%d,%d)", k, s.y0, s.y1,
+                          fine.cy0, fine.cy1);
+                rc = OFB_ERR_INVALID;
+            }
+        }
+        st->cum_dst.push_back(dst);
     }
     if (rc == OFB_OK) {
         void *p = nullptr;
@@ -633,7 +656,34 @@ int ofb_strips_result(const ofb_strips *st, int level, float **flow_own_d, float
     const size_t off = (size_t)(s.y0 - s.eb0) * s.w * 2;
     if (flow_own_d) *flow_own_d = st->flow[level] + off;
     // cumulative flow exists where a level writes it: every level but the coarsest (whose cumulative flow is its flow)
-    if (total_own_d) *total_own_d = (level < st->plan.levels - 1 ? st->cum[level] : st->flow[level]) + off;
+    if (total_own_d) *total_own_d = (st->plan.levels == 1 ? st->flow[level] : st->cum_dst[level]) + off;
+    return OFB_OK;
+}
+
+// Where the own rows [y0, y1) of level 0 live: a producer that writes them there and passes the same pointers to
+// ofb_strips_run_device saves the upload copy.
+int ofb_strips_input(const ofb_strips *st, uint8_t **prev_own_d, uint8_t **next_own_d, size_t *pitch)
+{
+    if (!st) {
+        set_error("strips_input: NULL handle");
+        return OFB_ERR_INVALID;
+    }
+    const LevelStrip &s = st->s[0];
+    const size_t off = (size_t)(s.y0 - s.eb0) * st->pitch[0];
+    if (prev_own_d) *prev_own_d = st->prev[0] + off;
+    if (next_own_d) *next_own_d = st->next[0] + off;
+    if (pitch) *pitch = st->pitch[0];
+    return OFB_OK;
+}
+
+// Whether level 0 also writes the total (cumulative) flow of the pair; on by default, 8 more bytes per pixel.
+int ofb_strips_set_total(ofb_strips *st, int on)
+{
+    if (!st) {
+        set_error("strips_set_total: NULL handle");
+        return OFB_ERR_INVALID;
+    }
+    st->want_total = on ? 1 : 0;
     return OFB_OK;
 }
 
@@ -665,10 +715,13 @@ int ofb_strips_run_device(ofb_strips *st, const uint8_t *prev_own_d, const uint8
     {
         const LevelStrip &s = st->s[0];
         const size_t off = (size_t)(s.y0 - s.eb0) * st->pitch[0];
-        OFB_CUDA_TRY(cudaMemcpy2DAsync(st->prev[0] + off, st->pitch[0], prev_own_d, pitch, (size_t)s.w, (size_t)(s.y1 - s.y0),
-                                       cudaMemcpyDeviceToDevice, q));
-        OFB_CUDA_TRY(cudaMemcpy2DAsync(st->next[0] + off, st->pitch[0], next_own_d, pitch, (size_t)s.w, (size_t)(s.y1 - s.y0),
-                                       cudaMemcpyDeviceToDevice, q));
+        // a producer that wrote the own rows in place (ofb_strips_input) saves this copy
+        if (prev_own_d != st->prev[0] + off)
+            OFB_CUDA_TRY(cudaMemcpy2DAsync(st->prev[0] + off, st->pitch[0], prev_own_d, pitch, (size_t)s.w, (size_t)(s.y1 - s.y0),
+                                           cudaMemcpyDeviceToDevice, q));
+        if (next_own_d != st->next[0] + off)
+            OFB_CUDA_TRY(cudaMemcpy2DAsync(st->next[0] + off, st->pitch[0], next_own_d, pitch, (size_t)s.w, (size_t)(s.y1 - s.y0),
+                                           cudaMemcpyDeviceToDevice, q));
     }
     OFB_CUDA_TRY(cudaMemsetAsync(st->overflow, 0, sizeof(int), q));
     // ONE image exchange, on level 0: the rows of my buffer that other ranks own (and vice versa), in place
@@ -716,23 +769,19 @@ int ofb_strips_run_device(ofb_strips *st, const uint8_t *prev_own_d, const uint8
     // pyramid: every buffer row of level k+1 from the buffer rows of level k (halo rows are built locally)
     for (int k = 0; k + 1 < L; k++) {
         const LevelStrip &s = st->s[k], &d = st->s[k + 1];
-        for (uint8_t *const *buf : {st->prev.data(), st->next.data()}) {
-            int rc = launch_pyr_down_strip(buf[k], st->pitch[k], s.w, s.eb1 - s.eb0, s.eb0, buf[k + 1], st->pitch[k + 1], d.eb0, d.eb1, q,
-                                           launches);
-            if (rc) return rc;
-        }
+        int rc = launch_pyr_down_strip(st->prev[k], st->pitch[k], s.w, s.eb1 - s.eb0, s.eb0, st->prev[k + 1], st->pitch[k + 1], d.eb0,
+                                       d.eb1, q, launches, 2, st->img_stride[k], st->img_stride[k + 1]);
+        if (rc) return rc;
     }
     // coarse to fine: rows [cy0, cy1) of cum_{k+1} into cum_in[k] (own part copied, the rest received), then the level
     for (int k = L - 1; k >= 0; k--) {
         const LevelStrip &s = st->s[k];
         if (k < L - 1) {
             const LevelStrip &up = st->s[k + 1];
-            const float *src = (k + 1 < L - 1) ? st->cum[k + 1] : st->flow[k + 1]; // cum of the coarsest level is its flow
-            const size_t rowf = (size_t)up.w * 2;                                  // floats per row
+            // level k+1 wrote its own rows of cum_{k+1} straight into cum_in[k] (cum_dst); the neighbours' rows follow
+            const float *src = st->cum_dst[k + 1]; // buffer-row indexing of level k+1 (origin up.eb0)
+            const size_t rowf = (size_t)up.w * 2;  // floats per row
             int lo, hi;
-            if (overlap(up.y0, up.y1, s.cy0, s.cy1, &lo, &hi))
-                OFB_CUDA_TRY(cudaMemcpyAsync(st->cum_in[k] + (size_t)(lo - s.cy0) * rowf, src + (size_t)(lo - up.eb0) * rowf,
-                                             (size_t)(hi - lo) * rowf * 4, cudaMemcpyDeviceToDevice, q));
             if (n) {
                 OFB_NCCL_TRY(n->GroupStart());
                 for (int peer = 0; peer < pl.world; peer++) {
@@ -786,8 +835,8 @@ int ofb_strips_run_device(ofb_strips *st, const uint8_t *prev_own_d, const uint8
         a.cum_h_local = std::max(s.cy1 - s.cy0, 1);
         a.cum_pair_stride = 0;
         a.flow_out = st->flow[k];
-        const bool want_cum = (k > 0 && k < L - 1) || (k == 0 && L > 1);
-        a.cum_out = want_cum ? st->cum[k] : nullptr;
+        const bool want_cum = k > 0 || (L > 1 && st->want_total); // every level but the finest feeds the next one
+        a.cum_out = want_cum ? st->cum_dst[k] : nullptr;
         a.flow_pair_stride = 0;
         a.reach_overflow = st->overflow;
         a.sm_count = ctx_sm_count(st->ctx);

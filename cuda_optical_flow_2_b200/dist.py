@@ -421,6 +421,25 @@ class NativeStrips:
             L.check(self.lib.ofb_strips_peer_connect(self._h, C.cast(blobs, C.c_void_p)))
             dist.barrier()  # nobody pushes before everybody has mapped its neighbours
 
+    def input_rows(self):
+        """(prev, next) uint8 torch views (own_rows, pitch) of where the own rows of level 0 live inside the runner:
+        fill them in place and pass them to run() to save the upload copy."""
+        C = self.C
+        pp, pn, pitch = C.c_void_p(), C.c_void_p(), C.c_size_t()
+        self.L.check(self.lib.ofb_strips_input(self._h, C.byref(pp), C.byref(pn), C.byref(pitch)))
+        y0, y1 = self.own_rows(0)
+
+        def view(ptr):
+            class _H:
+                __cuda_array_interface__ = {"shape": ((y1 - y0) * pitch.value,), "typestr": "|u1", "data": (ptr, False), "version": 3}
+
+            return self.torch.as_tensor(_H(), device=self.dev).view(y1 - y0, pitch.value)
+
+        return view(pp.value), view(pn.value)
+
+    def set_total(self, on: bool) -> None:
+        self.L.check(self.lib.ofb_strips_set_total(self._h, 1 if on else 0))
+
     def arena(self) -> int:
         p = self.C.c_void_p()
         self.L.check(self.lib.ofb_strips_peer_arena(self._h, self.C.byref(p)))

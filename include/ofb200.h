@@ -213,7 +213,10 @@ int ofb_stream_destroy(ofb_stream *s);
  *   ofb_strips_check          : synchronises; *overflow bit 0 = a warp sample reached past the halo rows, bit 1 = a
  *                               neighbour's rows did not arrive within 4 s (peer-memory transport)
  *   ofb_strips_run_device     : prev_own_d / next_own_d = rows [y0, y1) of level 0 (ofb_strips_own_rows), planar u8
- *   ofb_strips_result         : device pointers to the own rows of the residual flow / cumulative flow of a level */
+ *   ofb_strips_result         : device pointers to the own rows of the residual flow / cumulative flow of a level
+ *   ofb_strips_input          : where the own rows of level 0 live inside the handle: a producer that writes them there
+ *                               and passes the same pointers to ofb_strips_run_device saves the upload copy
+ *   ofb_strips_set_total      : whether level 0 also writes the total flow of the pair (default on) */
 typedef struct ofb_strips ofb_strips;
 int ofb_strips_nccl_unique_id(void *id128);
 int ofb_strips_create(ofb_ctx *ctx, int w, int h, int levels, int win, int warp_mode, float flow_scale, int world, int rank,
@@ -223,6 +226,8 @@ int ofb_strips_run_device(ofb_strips *s, const uint8_t *prev_own_d, const uint8_
 int ofb_strips_result(const ofb_strips *s, int level, float **flow_own_d, float **total_own_d);
 int ofb_strips_check(ofb_strips *s, void *stream, int *overflow);
 int ofb_strips_destroy(ofb_strips *s);
+int ofb_strips_input(const ofb_strips *s, uint8_t **prev_own_d, uint8_t **next_own_d, size_t *pitch);
+int ofb_strips_set_total(ofb_strips *s, int on);
 int ofb_strips_peer_handle(ofb_strips *s, void *blob128);
 int ofb_strips_peer_connect(ofb_strips *s, const void *blobs_world_x_128);
 int ofb_strips_peer_arena(ofb_strips *s, void **arena_d);

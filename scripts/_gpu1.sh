@@ -1,0 +1,1 @@
+timeout 600 python -m pytest tests/test_dist.py -x -q -m gpu 2>&1 | tail -15

@@ -1,0 +1,6 @@
+P=29511
+run() { python -m torch.distributed.run --nnodes=1 --nproc-per-node $1 --master-addr 127.0.0.1 --master-port $P scripts/run_strips.py --native --transport $2 --reps 200 $3 2>&1 | grep -E '^\{|Error|error' | tail -3; P=$((P+1)); }
+run $NG nccl --check
+run $NG peer --check
+run $NG peer ""
+run $NG nccl ""

@@ -20,6 +20,8 @@ ap.add_argument("--reps", type=int, default=10); ap.add_argument("--reach", type
 ap.add_argument("--check", action="store_true")
 ap.add_argument("--transport", default="gather", choices=["gather", "p2p", "nccl", "peer"], help="Python runner: one all-gather per exchange (gather) or grouped send/recv (p2p); --native: NCCL send/recv (nccl, default) or the sender's copy kernel into the receiver's memory over NVLink with epoch flags (peer)")
 ap.add_argument("--native", action="store_true", help="the native runner (csrc/strips.cu: C++ host side, NCCL send/recv between the ranks' buffers)")
+ap.add_argument("--total", action="store_true", help="--native: level 0 also writes the total flow of the pair (8 more bytes per pixel)")
+ap.add_argument("--copy-in", action="store_true", help="--native: the own rows are copied into the runner every pair instead of living there (ofb_strips_input)")
 ap.add_argument("--graph", action="store_true", help="capture one pair in a CUDA graph and replay it (1 GPU: works, -8 %; with NCCL exchanges the capture hung on this stack, PyTorch 2.11 + NCCL 2.28: unresolved)")
 a = ap.parse_args()
 world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0")); local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -44,9 +46,15 @@ rn = StripRunner(ctx, plan, rank, tp, dev, WARP_BILINEAR)
 s0 = rn.strips[0]
 pr, nr = prev[0, s0.y0:s0.y1, :a.w], nxt[0, s0.y0:s0.y1, :a.w]
 nat = NativeStrips(ctx, a.w, a.h, a.levels, a.win, world, rank, dev, WARP_BILINEAR, 1.0, a.reach, transport="peer" if a.transport == "peer" else "nccl") if a.native else None
+nin = (prev[0, s0.y0:s0.y1], nxt[0, s0.y0:s0.y1])
+if nat is not None:
+    nat.set_total(a.total)
+    if not a.copy_in:  # the producer writes the own rows where the runner keeps them
+        nin = nat.input_rows()
+        nin[0][:, :a.w].copy_(pr); nin[1][:, :a.w].copy_(nr)
 def one():
     if nat is not None:
-        nat.run(prev[0, s0.y0:s0.y1], nxt[0, s0.y0:s0.y1], torch.cuda.current_stream(dev).cuda_stream)
+        nat.run(nin[0], nin[1], torch.cuda.current_stream(dev).cuda_stream)
     else:
         rn.step(pr, nr)
 side = torch.cuda.Stream(dev)

@@ -240,11 +240,22 @@ def test_native_strips_peer_memory_transport_equals_whole_frame(ctx, oracle, W, 
             prev = oracle.make_frame(W, H, 0, 0, 8, 900 + trial)
             nxt = oracle.make_frame(W, H, dx, dy, 8, 900 + trial)
             dp, dn = planar_to_device(prev[None]), planar_to_device(nxt[None])
-            whole = ctx.flow_pairs_device(dp, dn, W, levels, win, warp_mode=WARP_BILINEAR)
+            total = torch.empty((1, H, W, 2), dtype=torch.float32, device=dev)
+            whole = ctx.flow_pairs_device(dp, dn, W, levels, win, warp_mode=WARP_BILINEAR, total_flow=total)
             torch.cuda.synchronize()
-            for rk, (ns, st) in enumerate(zip(ranks, streams)):
+            inputs = []
+            for ns in ranks:
                 y0, y1 = ns.own_rows(0)
-                ns.run(dp[0, y0:y1], dn[0, y0:y1], st.cuda_stream)
+                if trial == 1:  # the producer writes the own rows in place: no upload copy
+                    pin, nin = ns.input_rows()
+                    pin[:, :W].copy_(dp[0, y0:y1, :W])
+                    nin[:, :W].copy_(dn[0, y0:y1, :W])
+                    inputs.append((pin, nin))
+                else:
+                    inputs.append((dp[0, y0:y1], dn[0, y0:y1]))
+            torch.cuda.synchronize()  # (no host synchronisation between the ranks' run() calls: a rank waits for its neighbours)
+            for ns, st, (pin, nin) in zip(ranks, streams, inputs):
+                ns.run(pin, nin, st.cuda_stream)
             for ns, st in zip(ranks, streams):
                 ns.check(st.cuda_stream)
             for ns in ranks:
@@ -254,6 +265,11 @@ def test_native_strips_peer_memory_transport_equals_whole_frame(ctx, oracle, W, 
                     m = ~torch.isnan(ref)
                     assert torch.equal(torch.isnan(ref), torch.isnan(got)) and torch.equal(ref[m], got[m]), \
                         f"pair {trial} rank {ns.rank} level {k}"
+                y0, y1 = ns.own_rows(0)
+                ref, got = total[0, y0:y1], ns.own_flow(0, total=True)
+                m = ~torch.isnan(ref)
+                assert torch.equal(torch.isnan(ref), torch.isnan(got)) and torch.equal(ref[m], got[m]), \
+                    f"pair {trial} rank {ns.rank} total flow"
     finally:
         torch.cuda.synchronize()
         for ns in ranks:
