@@ -144,7 +144,9 @@ struct ArenaLayout {
     size_t prev0, next0, cum_in[OFB_MAX_LEVELS], flags, bytes;
     // flags (unsigned): arrive[x * world + src] = epoch of the last exchange x that src completed into this arena;
     //                   done[src] at L * world + src = last epoch rank src finished reading what this rank pushed;
-    //                   counter[x] at (L + 1) * world + x: blocks of this rank's push kernel that have finished (local).
+    //                   counter[x] at (L + 1) * world + x: blocks of this rank's push kernel that have finished (local);
+    //                   pairs at (L + 1) * world + L: pairs this rank has completed (local).  The epoch of a pair is
+    //                   pairs + 1, read from here by the kernels, so that a captured CUDA graph of one pair replays.
 };
 static ArenaLayout arena_layout(const StripPlan &pl, int rank)
 {
@@ -160,7 +162,7 @@ static ArenaLayout arena_layout(const StripPlan &pl, int rank)
     a.prev0 = take(pitch0 * (v[0].eb1 - v[0].eb0));
     a.next0 = take(pitch0 * (v[0].eb1 - v[0].eb0));
     for (int k = 0; k < pl.levels; k++) a.cum_in[k] = take((size_t)(v[k].w >> 1) * std::max(v[k].cy1 - v[k].cy0, 1) * 8);
-    a.flags = take(((size_t)(pl.levels + 1) * pl.world + pl.levels) * sizeof(unsigned));
+    a.flags = take(((size_t)(pl.levels + 1) * pl.world + pl.levels + 1) * sizeof(unsigned));
     a.bytes = off;
     return a;
 }
@@ -176,19 +178,19 @@ struct PeerPushArgs {
     unsigned *arrive[PEER_MAX_DST];           // arrive[x * world + me] in the arena of each destination
     const unsigned *done_local[PEER_MAX_DST]; // done[dst] in MY arena: dst has finished with what I pushed last pair
     unsigned *counter;                        // counter[x] in my arena
-    unsigned epoch;
+    const unsigned *pairs;                    // pairs completed (my arena): this pair's epoch is *pairs + 1
     int *err;
 };
 struct PeerWaitArgs {
     const unsigned *flag[PEER_MAX_DST]; // arrive[x * world + src] in my arena
     int n;
-    unsigned epoch;
+    const unsigned *pairs;
     int *err;
 };
 struct PeerDoneArgs {
     unsigned *flag[2 * PEER_MAX_DST]; // done[me] in the arena of every rank that pushes to me
     int n;
-    unsigned epoch;
+    unsigned *pairs;
 };
 constexpr unsigned long long PEER_TIMEOUT_NS = 4000000000ull; // a peer that never shows up: flag the pair, do not hang
 
@@ -219,7 +221,8 @@ __device__ bool peer_spin(const unsigned *p, unsigned epoch)
 // the destinations' arenas (peer stores over NVLink), and -- last block out -- raise the epoch flag in each of them.
 __global__ void __launch_bounds__(256) peer_push_kernel(const __grid_constant__ PeerPushArgs a)
 {
-    if (threadIdx.x < a.ndst && !peer_spin(a.done_local[threadIdx.x], a.epoch - 1u)) atomicOr(a.err, 2);
+    const unsigned epoch = *a.pairs + 1u;
+    if (threadIdx.x < a.ndst && !peer_spin(a.done_local[threadIdx.x], epoch - 1u)) atomicOr(a.err, 2);
     __syncthreads();
     const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nt = (size_t)gridDim.x * blockDim.x;
     for (int s = 0; s < a.nseg; s++) {
@@ -241,20 +244,23 @@ __global__ void __launch_bounds__(256) peer_push_kernel(const __grid_constant__ 
         if (arrived == gridDim.x - 1) {
             *a.counter = 0u;
             __threadfence_system();
-            for (int d = 0; d < a.ndst; d++) asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(a.arrive[d]), "r"(a.epoch) : "memory");
+            for (int d = 0; d < a.ndst; d++) asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(a.arrive[d]), "r"(epoch) : "memory");
         }
     }
 }
 // Receiver side: one thread per source spins on its epoch flag.
 __global__ void peer_wait_kernel(const __grid_constant__ PeerWaitArgs a)
 {
-    if (threadIdx.x < a.n && !peer_spin(a.flag[threadIdx.x], a.epoch)) atomicOr(a.err, 2);
+    if (threadIdx.x < a.n && !peer_spin(a.flag[threadIdx.x], *a.pairs + 1u)) atomicOr(a.err, 2);
     __threadfence_system();
 }
-// End of a pair: tell every rank that pushes to me that its rows have been used.
+// End of a pair: tell every rank that pushes to me that its rows have been used, and count the pair.
 __global__ void peer_done_kernel(const __grid_constant__ PeerDoneArgs a)
 {
-    if (threadIdx.x < a.n) asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(a.flag[threadIdx.x]), "r"(a.epoch) : "memory");
+    const unsigned epoch = *a.pairs + 1u;
+    if (threadIdx.x < a.n) asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(a.flag[threadIdx.x]), "r"(epoch) : "memory");
+    __syncthreads();
+    if (threadIdx.x == 0) *a.pairs = epoch;
 }
 } // namespace ofb
 
@@ -284,7 +290,6 @@ struct ofb_strips {
     std::vector<ArenaLayout> peer_lay;
     std::vector<void *> ipc_opened;
     bool peers_connected = false;
-    unsigned epoch = 0;
 };
 
 namespace {
@@ -315,10 +320,11 @@ inline unsigned *flag_ptr(uint8_t *arena, const ArenaLayout &lay, size_t index)
     return reinterpret_cast<unsigned *>(arena + lay.flags) + index;
 }
 // Exchange x of the pair with epoch `epoch`: push `sends`, then wait for the ranks in `sources`.
-int peer_exchange(ofb_strips *st, int x, unsigned epoch, const std::vector<PeerSend> &sends, const std::vector<int> &sources,
-                  cudaStream_t q, unsigned long long *launches)
+int peer_exchange(ofb_strips *st, int x, const std::vector<PeerSend> &sends, const std::vector<int> &sources, cudaStream_t q,
+                  unsigned long long *launches)
 {
     const int world = st->plan.world, L = st->plan.levels, me = st->rank;
+    unsigned *pairs = flag_ptr(st->arena, st->lay, (size_t)(L + 1) * world + L);
     if (!sends.empty()) {
         PeerPushArgs a{};
         size_t total = 0;
@@ -342,7 +348,7 @@ int peer_exchange(ofb_strips *st, int x, unsigned epoch, const std::vector<PeerS
             }
         }
         a.counter = flag_ptr(st->arena, st->lay, (size_t)(L + 1) * world + x);
-        a.epoch = epoch;
+        a.pairs = pairs;
         a.err = st->overflow;
         const unsigned blocks = (unsigned)std::min<size_t>(64, std::max<size_t>(1, total / (256 * 64)));
         peer_push_kernel<<<blocks, 256, 0, q>>>(a);
@@ -358,7 +364,7 @@ int peer_exchange(ofb_strips *st, int x, unsigned epoch, const std::vector<PeerS
             }
             w.flag[w.n++] = flag_ptr(st->arena, st->lay, (size_t)x * world + src);
         }
-        w.epoch = epoch;
+        w.pairs = pairs;
         w.err = st->overflow;
         peer_wait_kernel<<<1, 32, 0, q>>>(w);
         OFB_CUDA_TRY(cudaGetLastError());
@@ -706,7 +712,6 @@ int ofb_strips_run_device(ofb_strips *st, const uint8_t *prev_own_d, const uint8
     NcclApi *n = pl.world > 1 && !peer_mode ? nccl() : nullptr;
     unsigned long long *launches = ctx_launch_counter(st->ctx);
     const int L = pl.levels, me = st->rank;
-    const unsigned epoch = ++st->epoch;
     std::vector<int> all_sources; // every rank that pushes to me during the pair
     if (pitch < (size_t)pl.W) {
         set_error("strips_run: pitch %zu smaller than the width %d", pitch, pl.W);
@@ -763,7 +768,7 @@ int ofb_strips_run_device(ofb_strips *st, const uint8_t *prev_own_d, const uint8
                 add_unique(all_sources, peer);
             }
         }
-        int rc = peer_exchange(st, 0, epoch, sends, sources, q, launches);
+        int rc = peer_exchange(st, 0, sends, sources, q, launches);
         if (rc) return rc;
     }
     // pyramid: every buffer row of level k+1 from the buffer rows of level k (halo rows are built locally)
@@ -809,7 +814,7 @@ int ofb_strips_run_device(ofb_strips *st, const uint8_t *prev_own_d, const uint8
                         add_unique(all_sources, peer);
                     }
                 }
-                int rc = peer_exchange(st, L - 1 - k, epoch, sends, sources, q, launches); // exchanges 1 .. L-1
+                int rc = peer_exchange(st, L - 1 - k, sends, sources, q, launches); // exchanges 1 .. L-1
                 if (rc) return rc;
             }
         }
@@ -843,7 +848,7 @@ int ofb_strips_run_device(ofb_strips *st, const uint8_t *prev_own_d, const uint8
         int rc = launch_lk_level(a, q, launches);
         if (rc) return rc;
     }
-    if (peer_mode && !all_sources.empty()) { // the rows my neighbours pushed have been used: they may push the next pair's
+    if (peer_mode) { // the rows my neighbours pushed have been used: they may push the next pair's
         PeerDoneArgs d{};
         for (int src : all_sources) {
             if (d.n == 2 * PEER_MAX_DST) {
@@ -852,7 +857,7 @@ int ofb_strips_run_device(ofb_strips *st, const uint8_t *prev_own_d, const uint8
             }
             d.flag[d.n++] = flag_ptr(st->peer_arena[src], st->peer_lay[src], (size_t)L * pl.world + me);
         }
-        d.epoch = epoch;
+        d.pairs = flag_ptr(st->arena, st->lay, (size_t)(L + 1) * pl.world + L);
         peer_done_kernel<<<1, 32, 0, q>>>(d);
         OFB_CUDA_TRY(cudaGetLastError());
         if (launches) ++*launches;

@@ -274,3 +274,62 @@ def test_native_strips_peer_memory_transport_equals_whole_frame(ctx, oracle, W, 
         torch.cuda.synchronize()
         for ns in ranks:
             ns.close()
+
+
+@pytest.mark.gpu
+def test_native_strips_peer_memory_pair_replays_as_cuda_graph(ctx, oracle):
+    """The peer-memory transport has no host-side state per pair (the epoch lives in device memory), so one pair of a
+    rank is capturable as a CUDA graph; the replays stay bit for bit the whole-frame result."""
+    import torch
+
+    from cuda_optical_flow_2_b200 import WARP_BILINEAR, planar_to_device
+    from cuda_optical_flow_2_b200.dist import NativeStrips
+
+    W, H, levels, win, world = 1280, 720, 3, 9, 2
+    dev = torch.device("cuda", 0)
+    ranks = [NativeStrips(ctx, W, H, levels, win, world, rk, dev, WARP_BILINEAR, 1.0, 16, transport="local") for rk in range(world)]
+    streams = [torch.cuda.Stream(dev) for _ in range(world)]
+    try:
+        NativeStrips.connect_local(ranks)
+        ins = [ns.input_rows() for ns in ranks]
+
+        def load(seed, dx, dy):
+            prev = oracle.make_frame(W, H, 0, 0, 8, seed)
+            nxt = oracle.make_frame(W, H, dx, dy, 8, seed)
+            dp, dn = planar_to_device(prev[None]), planar_to_device(nxt[None])
+            for ns, (pin, nin) in zip(ranks, ins):
+                y0, y1 = ns.own_rows(0)
+                pin[:, :W].copy_(dp[0, y0:y1, :W])
+                nin[:, :W].copy_(dn[0, y0:y1, :W])
+            whole = ctx.flow_pairs_device(dp, dn, W, levels, win, warp_mode=WARP_BILINEAR)
+            torch.cuda.synchronize()
+            return whole
+
+        load(11, 1.0, 1.0)
+        for ns, st, (pin, nin) in zip(ranks, streams, ins):  # warm-up pair, eager
+            ns.run(pin, nin, st.cuda_stream)
+        torch.cuda.synchronize()
+        graphs = []
+        for ns, st, (pin, nin) in zip(ranks, streams, ins):
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=st, capture_error_mode="thread_local"):
+                ns.run(pin, nin, torch.cuda.current_stream(dev).cuda_stream)
+            graphs.append(g)
+        for trial, (dx, dy) in enumerate([(2.25, -1.5), (-3.0, 0.75)]):
+            whole = load(20 + trial, dx, dy)
+            for g, st in zip(graphs, streams):  # each rank on its own stream: a rank waits for its neighbour
+                with torch.cuda.stream(st):
+                    g.replay()
+            torch.cuda.synchronize()
+            for ns in ranks:
+                ns.check(0)
+                for k in range(levels):
+                    y0, y1 = ns.own_rows(k)
+                    ref, got = whole[k][0, y0:y1], ns.own_flow(k)
+                    m = ~torch.isnan(ref)
+                    assert torch.equal(torch.isnan(ref), torch.isnan(got)) and torch.equal(ref[m], got[m]), \
+                        f"replay {trial} rank {ns.rank} level {k}"
+    finally:
+        torch.cuda.synchronize()
+        for ns in ranks:
+            ns.close()
