@@ -333,6 +333,18 @@ def main_b200(args):
     e2e_value = (W * H / 1e6) * Be * world * e2e_steps / te.item()
     h2d = int(hprev.nbytes + hnext.nbytes)
     d2h = int(sum(a.nbytes for a in houts))
+    # what bounds e2e: the device-to-host link.  One plain pinned copy of the level-0 flow buffer, timed the same way.
+    pcie_d2h = None
+    if rank == 0:
+        src = flows[0][:Be].contiguous() if B >= Be else flows[0]
+        dst = torch.from_numpy(houts[0].reshape(-1)[:src.numel()])
+        dst.copy_(src.reshape(-1))
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            dst.copy_(src.reshape(-1), non_blocking=True)
+        torch.cuda.synchronize()
+        pcie_d2h = 3 * src.numel() * 4 / (time.perf_counter() - t0) / 1e9
     for p in [p1, p2] + pouts:
         lib.ofb_host_free(p)
 
@@ -371,7 +383,10 @@ def main_b200(args):
                            "frames per step, fresh outputs each level)", "parallelism": f"frame-batch x{world}"},
                 "roofline": roofline, "cpu_baseline": cpu,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                        "pairs_per_step": Be, "layout": "reference 3-channel u8 in, float2 flow of every level out"},
+                        "pairs_per_step": Be, "layout": "reference 3-channel u8 in, float2 flow of every level out",
+                        "d2h_gbs_achieved": d2h * world * e2e_steps / te.item() / 1e9 / world,
+                        "d2h_gbs_plain_copy": pcie_d2h,
+                        "bound": "PCIe device-to-host: 10.5 B of flow per pixel leave the GPU, 6 B of frames enter"},
                 "gpu_launches": int(launches), "clocks": clocks}
         print(json.dumps(line), flush=True)
     if world > 1:

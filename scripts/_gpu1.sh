@@ -1,2 +1,3 @@
-timeout 600 python -m pytest tests/test_dist.py -x -q -m gpu -k "graph" 2>&1 | tail -8
-python scripts/run_strips.py --native --reps 200 --check --graph 2>&1 | grep -E '^\{|rror' | cut -c1-330
+timeout 300 python bench.py > gpurun_out/bench_r1.json 2> gpurun_out/bench_r1.err; tail -c 900 gpurun_out/bench_r1.json; tail -3 gpurun_out/bench_r1.err
+timeout 300 python bench.py --pairs 1024 --steps 5 --no-cpu-baseline 2>&1 | tail -1 | cut -c1-400
+timeout 300 python bench.py --pairs 512 --steps 10 --no-cpu-baseline 2>&1 | tail -1 | cut -c1-400
