@@ -1,3 +1,2 @@
-timeout 300 python bench.py > gpurun_out/bench_r1.json 2> gpurun_out/bench_r1.err; tail -c 900 gpurun_out/bench_r1.json; tail -3 gpurun_out/bench_r1.err
-timeout 300 python bench.py --pairs 1024 --steps 5 --no-cpu-baseline 2>&1 | tail -1 | cut -c1-400
-timeout 300 python bench.py --pairs 512 --steps 10 --no-cpu-baseline 2>&1 | tail -1 | cut -c1-400
+timeout 600 python -m pytest tests/test_gpu_parity.py tests/test_dist.py -x -q -m gpu 2>&1 | tail -4
+timeout 300 python bench.py --steps 10 --no-cpu-baseline 2>&1 | tail -1 | python -c "import json,sys; d=json.loads(sys.stdin.read()); print(d['value'], d['ms_per_step'], d['roofline']['avg_launch_ms'], d['roofline']['frac'], d['roofline']['step_share'])"
