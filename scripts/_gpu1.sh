@@ -1,2 +1,7 @@
-timeout 600 python -m pytest tests/test_gpu_parity.py tests/test_dist.py -x -q -m gpu 2>&1 | tail -4
-timeout 300 python bench.py --steps 10 --no-cpu-baseline 2>&1 | tail -1 | python -c "import json,sys; d=json.loads(sys.stdin.read()); print(d['value'], d['ms_per_step'], d['roofline']['avg_launch_ms'], d['roofline']['frac'], d['roofline']['step_share'])"
+CMD="python bench.py --steps 2 --warmup 3 --no-cpu-baseline"
+$CMD > gpurun_out/plain.log 2>&1 &&
+ncu --metrics gpu__time_duration.sum --clock-control none --kernel-name-base demangled -k regex:ofb:: --csv --log-file gpurun_out/r1_launches_final.csv $CMD > gpurun_out/ncu1.log 2>&1
+echo "launch list rc=$?"
+ncu --set full --clock-control none --import-source on --kernel-name-base mangled -k regex:lk_level_kernelILi9ELi2ELb0E -s 3 -c 1 -f -o gpurun_out/r1_lk_level0_final $CMD > gpurun_out/ncu2.log 2>&1
+echo "set full rc=$?"
+tail -3 gpurun_out/ncu2.log
