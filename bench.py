@@ -286,7 +286,7 @@ def main_b200(args):
 
     # ---- latency of ONE pair (BASELINE configs[1] as the reference's frame loop meets it): device-resident,
     #      back-to-back calls on the stream; reported beside the batched throughput, not instead of it
-    one_ms = None
+    one_ms = one_graph_ms = None
     if rank == 0:
         f1 = [f[:1] for f in flows]
         for _ in range(5):
@@ -298,6 +298,26 @@ def main_b200(args):
         e1.record()
         torch.cuda.synchronize()
         one_ms = e0.elapsed_time(e1) / 50
+        # the same call captured once as a CUDA graph and replayed (no allocation, no host state per call)
+        try:
+            side = torch.cuda.Stream(dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=side):
+                ctx.flow_pairs_device(prev[:1], nxt[:1], W, LEVELS, WIN, warp_mode=WARP_BILINEAR, flows=f1,
+                                      stream=torch.cuda.current_stream(dev).cuda_stream)
+            for _ in range(5):
+                g.replay()
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(50):
+                g.replay()
+            e1.record()
+            torch.cuda.synchronize()
+            one_graph_ms = e0.elapsed_time(e1) / 50
+        except Exception as ex:  # reported, never fatal
+            one_graph_ms = None
+            print(f"single-pair graph capture failed: {ex!r}", file=sys.stderr)
 
     # ---- end to end through the host-pointer C-ABI call (rank-local, all ranks run it concurrently)
     Be = args.e2e_pairs
@@ -379,7 +399,7 @@ def main_b200(args):
                 "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "u8 -> int32 sums -> f64 solve -> f32 flow", "data": "synthetic",
                 "config": {"workload": "1920x1080 pair, 3-level Gaussian pyramid, 9x9 window, bilinear warp",
-                           "pairs_per_gpu_per_step": B, "single_pair_latency_ms": one_ms, "l2": f"inputs exceed L2 ({B * 2 * pitch * H / 1e6:.0f} MB of "
+                           "pairs_per_gpu_per_step": B, "single_pair_latency_ms": one_ms, "single_pair_latency_ms_cuda_graph": one_graph_ms, "l2": f"inputs exceed L2 ({B * 2 * pitch * H / 1e6:.0f} MB of "
                            "frames per step, fresh outputs each level)", "parallelism": f"frame-batch x{world}"},
                 "roofline": roofline, "cpu_baseline": cpu,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

@@ -200,12 +200,17 @@ static int run_pairs_device(ofb_ctx *c, const ofb_params *p, const PairPlan &pl,
         pn[k] = base + pl.off_next[k];
         pitch[k] = pl.pitch[k];
         istr[k] = pl.istride[k];
+        // both frames of every pair in one launch
+        const bool one = 2 * n <= 65535; // grid.z limit
         int rc = launch_pyr_down(pp[k - 1], pitch[k - 1], istr[k - 1], pl.w[k - 1], pl.h[k - 1],
-                                 const_cast<uint8_t *>(pp[k]), pitch[k], istr[k], n, 1, st, &c->launches);
+                                 const_cast<uint8_t *>(pp[k]), pitch[k], istr[k], n, 1, st, &c->launches, one ? pn[k - 1] : nullptr,
+                                 one ? const_cast<uint8_t *>(pn[k]) : nullptr);
         if (rc) return rc;
-        rc = launch_pyr_down(pn[k - 1], pitch[k - 1], istr[k - 1], pl.w[k - 1], pl.h[k - 1], const_cast<uint8_t *>(pn[k]),
-                             pitch[k], istr[k], n, 1, st, &c->launches);
-        if (rc) return rc;
+        if (!one) {
+            rc = launch_pyr_down(pn[k - 1], pitch[k - 1], istr[k - 1], pl.w[k - 1], pl.h[k - 1], const_cast<uint8_t *>(pn[k]),
+                                 pitch[k], istr[k], n, 1, st, &c->launches);
+            if (rc) return rc;
+        }
     }
     if (L > 1) {
         int rc = prof_end(c, st);

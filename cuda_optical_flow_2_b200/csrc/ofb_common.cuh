@@ -53,7 +53,7 @@ int preload_pyramid();
 // ---- pyramid (pyramid.cu) ------------------------------------------------------------------
 int launch_pyr_down(const uint8_t *src, size_t src_pitch, size_t src_stride, int sw, int sh, uint8_t *dst,
                     size_t dst_pitch, size_t dst_stride, int n_images, int channels, cudaStream_t stream,
-                    unsigned long long *launches);
+                    unsigned long long *launches, const uint8_t *src2 = nullptr, uint8_t *dst2 = nullptr);
 
 int launch_pyr_down_strip(const uint8_t *src, size_t src_pitch, int sw, int src_rows, int src_y_off, uint8_t *dst,
                           size_t dst_pitch, int dst_y0, int dst_y1, cudaStream_t stream, unsigned long long *launches,

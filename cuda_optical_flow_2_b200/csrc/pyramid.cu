@@ -30,14 +30,21 @@ __device__ __forceinline__ void pyr_hrow(const uint4 q, uint32_t left, uint32_t 
 __global__ void __launch_bounds__(256)
 pyr_down_planar_kernel(const uint8_t *__restrict__ src, size_t src_pitch, size_t src_stride, int dw, int dh,
                        uint8_t *__restrict__ dst, size_t dst_pitch, size_t dst_stride, int src_y_off, int dst_y0,
-                       int src_rows)
+                       int src_rows, const uint8_t *__restrict__ src2, uint8_t *__restrict__ dst2, int n_first)
 {
+    // images n_first .. of the launch form a second batch with its own base pointers (prev and next frames of the
+    // pairs in one launch)
+    const int zi = (int)blockIdx.z < n_first ? (int)blockIdx.z : (int)blockIdx.z - n_first;
+    if ((int)blockIdx.z >= n_first) {
+        src = src2;
+        dst = dst2;
+    }
     const int tx = blockIdx.x * 32 + threadIdx.x;
     const int x0 = 8 * tx;
     const int y = 2 * (blockIdx.y * 8 + threadIdx.y);
     // whole warps stay alive for the shuffle; lanes past the row only skip their loads and stores
     const bool live = x0 < dw && y < dh;
-    const uint8_t *s = src + (size_t)blockIdx.z * src_stride;
+    const uint8_t *s = src + (size_t)zi * src_stride;
     const bool two = y + 1 < dh;
     uint32_t h[5][4];
 #pragma unroll
@@ -60,7 +67,7 @@ pyr_down_planar_kernel(const uint8_t *__restrict__ src, size_t src_pitch, size_t
         for (int i = 0; i < 4; i++) v[i] = ((h[2 * o][i] + 2 * h[2 * o + 1][i] + h[2 * o + 2][i]) >> 4) & 0x00ff00ffu;
         // v[i] holds outputs 2i (low half) and 2i+1 (high half), each already < 256
         const uint32_t lo = __byte_perm(v[0], v[1], 0x6420), hi = __byte_perm(v[2], v[3], 0x6420);
-        uint8_t *d = dst + (size_t)blockIdx.z * dst_stride + (size_t)(y + o) * dst_pitch + x0;
+        uint8_t *d = dst + (size_t)zi * dst_stride + (size_t)(y + o) * dst_pitch + x0;
         if (x0 + 7 < dw && (reinterpret_cast<uintptr_t>(d) & 7) == 0) {
             *reinterpret_cast<uint2 *>(d) = make_uint2(lo, hi);
         } else {
@@ -130,7 +137,7 @@ int launch_pyr_down_strip(const uint8_t *src, size_t src_pitch, int sw, int src_
     }
     dim3 grid((unsigned)((dw + 255) / 256), (unsigned)((dh + 15) / 16), (unsigned)n_images);
     pyr_down_planar_kernel<<<grid, block, 0, stream>>>(src, src_pitch, src_stride, dw, dh, dst, dst_pitch, dst_stride, src_y_off,
-                                                       dst_y0, src_rows);
+                                                       dst_y0, src_rows, nullptr, nullptr, n_images);
     OFB_CUDA_TRY(cudaGetLastError());
     if (launches) ++*launches;
     return OFB_OK;
@@ -138,9 +145,14 @@ int launch_pyr_down_strip(const uint8_t *src, size_t src_pitch, int sw, int src_
 
 int launch_pyr_down(const uint8_t *src, size_t src_pitch, size_t src_stride, int sw, int sh, uint8_t *dst,
                     size_t dst_pitch, size_t dst_stride, int n_images, int channels, cudaStream_t stream,
-                    unsigned long long *launches)
+                    unsigned long long *launches, const uint8_t *src2, uint8_t *dst2)
 {
+    // src2 / dst2 (planar only): a second batch of n_images with the same geometry in the same launch
     const int dw = sw >> 1, dh = sh >> 1;
+    if (src2 && (channels != 1 || !dst2 || (reinterpret_cast<uintptr_t>(src2) & 15))) {
+        set_error("pyr_down: the second batch needs planar, 16-byte aligned images");
+        return OFB_ERR_INVALID;
+    }
     if (dw < 1 || dh < 1 || n_images < 1 || (channels != 1 && channels != 3)) {
         set_error("pyr_down: bad geometry (src %dx%d, %d images, %d channels)", sw, sh, n_images, channels);
         return OFB_ERR_INVALID;
@@ -150,14 +162,15 @@ int launch_pyr_down(const uint8_t *src, size_t src_pitch, size_t src_stride, int
             set_error("pyr_down: planar source images need 16-byte aligned rows (pitch, base and image stride)");
             return OFB_ERR_INVALID;
         }
-        if (n_images > 65535) {
+        const int nz = src2 ? 2 * n_images : n_images;
+        if (nz > 65535) {
             set_error("pyr_down: at most 65535 images per launch");
             return OFB_ERR_INVALID;
         }
         dim3 block(32, 8);
-        dim3 grid((unsigned)((dw + 255) / 256), (unsigned)((dh + 15) / 16), (unsigned)n_images);
+        dim3 grid((unsigned)((dw + 255) / 256), (unsigned)((dh + 15) / 16), (unsigned)nz);
         pyr_down_planar_kernel<<<grid, block, 0, stream>>>(src, src_pitch, src_stride, dw, dh, dst, dst_pitch, dst_stride, 0, 0,
-                                                           sh);
+                                                           sh, src2, dst2, n_images);
         OFB_CUDA_TRY(cudaGetLastError());
         if (launches) ++*launches;
     } else {

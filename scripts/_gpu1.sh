@@ -1,7 +1,4 @@
-CMD="python bench.py --steps 2 --warmup 3 --no-cpu-baseline"
-$CMD > gpurun_out/plain.log 2>&1 &&
-ncu --metrics gpu__time_duration.sum --clock-control none --kernel-name-base demangled -k regex:ofb:: --csv --log-file gpurun_out/r1_launches_final.csv $CMD > gpurun_out/ncu1.log 2>&1
-echo "launch list rc=$?"
-ncu --set full --clock-control none --import-source on --kernel-name-base mangled -k regex:lk_level_kernelILi9ELi2ELb0E -s 3 -c 1 -f -o gpurun_out/r1_lk_level0_final $CMD > gpurun_out/ncu2.log 2>&1
-echo "set full rc=$?"
-tail -3 gpurun_out/ncu2.log
+timeout 600 python -m pytest tests -x -q -m gpu 2>&1 | tail -4
+timeout 300 python bench.py --steps 10 > gpurun_out/bench_r1.json 2> gpurun_out/bench_r1.err; tail -3 gpurun_out/bench_r1.err; python -c "
+import json; d=json.loads(open('gpurun_out/bench_r1.json').read().strip().splitlines()[-1])
+print(d['value'], d['ms_per_step'], d['roofline']['frac'], d['config'], d['e2e']['value'], d['gpu_launches'], d['roofline']['step_share'])"
