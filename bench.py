@@ -282,6 +282,10 @@ def main_b200(args):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_step = t.item() / args.steps
+    if world > 1:  # kernels launched inside the timed region, all ranks
+        lt = torch.tensor([launches], dtype=torch.int64, device=dev)
+        dist.all_reduce(lt, op=dist.ReduceOp.SUM)
+        launches = int(lt.item())
     value = (W * H / 1e6) * B * world / (ms_step / 1e3)
 
     # ---- latency of ONE pair (BASELINE configs[1] as the reference's frame loop meets it): device-resident,
