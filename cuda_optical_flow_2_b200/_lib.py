@@ -72,6 +72,7 @@ SIGNATURES = {
     "ofb_stream_create": (C.c_int, [_vp, C.POINTER(OfbParams), C.c_int, C.c_double, C.c_double, C.POINTER(_vp)]),
     "ofb_stream_push_bgr_host": (C.c_int, [_vp, u8p, C.POINTER(f32p), f32p, i32p]),
     "ofb_stream_destroy": (C.c_int, [_vp]),
+    "ofb_strips_plan_query": (C.c_int, [C.c_int] * 8 + [i32p]),
     "ofb_strips_nccl_unique_id": (C.c_int, [_vp]),
     "ofb_strips_create": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, C.c_int, C.c_int,
                                     _vp, C.POINTER(_vp)]),

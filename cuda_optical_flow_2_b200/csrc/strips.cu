@@ -380,6 +380,34 @@ void add_unique(std::vector<int> &v, int x)
 
 extern "C" {
 
+// The strip schedule as this library computes it, without a device: rows of `level` on `rank` as
+// out8 = {y0, y1, by0, by1, cy0, cy1, eb0, eb1} (own rows; rows the level kernel needs; rows of the next-coarser
+// cumulative flow held; rows the image buffers hold, which adds what building the coarser levels' halo rows locally
+// takes).  Lets a host check its own partitioning -- and the tests check cuda_optical_flow_2_b200/dist.py -- against it.
+int ofb_strips_plan_query(int w, int h, int levels, int win, int world, int rank, int reach, int level, int *out8)
+{
+    if (!out8 || w < 1 || h < 1 || levels < 1 || levels > OFB_MAX_LEVELS || (win & 1) == 0 || win < 3 || win > OFB_MAX_WINDOW ||
+        world < 1 || rank < 0 || rank >= world || reach < 0 || level < 0 || level >= levels) {
+        set_error("strips_plan_query: bad arguments");
+        return OFB_ERR_INVALID;
+    }
+    const int hc = h >> (levels - 1);
+    if (hc < world || (w >> (levels - 1)) < 1) {
+        set_error("coarsest level has %d rows, cannot cut it into %d strips", hc, world);
+        return OFB_ERR_INVALID;
+    }
+    StripPlan pl;
+    pl.W = w, pl.H = h, pl.levels = levels, pl.win = win, pl.world = world, pl.reach = reach;
+    pl.r = win / 2;
+    pl.img_halo = pl.r + 2 + reach + 2;
+    for (int rk = 0; rk < world; rk++) pl.coarse_bounds.push_back((int)(((long long)rk * hc) / world));
+    pl.coarse_bounds.push_back(hc);
+    const LevelStrip s = pl.strips(rank)[level];
+    const int v[8] = {s.y0, s.y1, s.by0, s.by1, s.cy0, s.cy1, s.eb0, s.eb1};
+    memcpy(out8, v, sizeof v);
+    return OFB_OK;
+}
+
 int ofb_strips_nccl_unique_id(void *id128)
 {
     NcclApi *n = nccl();

@@ -208,6 +208,7 @@ int ofb_stream_destroy(ofb_stream *s);
  *                      then a copy kernel of the sender that stores the rows into the receiver's memory over NVLink
  *                      and raises an epoch flag there, plus a one-block wait kernel on the receiver's stream.
  *                      ofb_strips_peer_connect_local does the same for ranks living in one process.
+ *   ofb_strips_plan_query     : host only, no device: the rows {y0, y1, by0, by1, cy0, cy1, eb0, eb1} of a level on a rank
  *   ofb_strips_nccl_unique_id : rank 0 makes the 128-byte id, the application broadcasts it (any transport)
  *   ofb_strips_create         : collective over all ranks when a NCCL id is given (ncclCommInitRank)
  *   ofb_strips_check          : synchronises; *overflow bit 0 = a warp sample reached past the halo rows, bit 1 = a
@@ -218,6 +219,7 @@ int ofb_stream_destroy(ofb_stream *s);
  *                               and passes the same pointers to ofb_strips_run_device saves the upload copy
  *   ofb_strips_set_total      : whether level 0 also writes the total flow of the pair (default on) */
 typedef struct ofb_strips ofb_strips;
+int ofb_strips_plan_query(int w, int h, int levels, int win, int world, int rank, int reach, int level, int *out8);
 int ofb_strips_nccl_unique_id(void *id128);
 int ofb_strips_create(ofb_ctx *ctx, int w, int h, int levels, int win, int warp_mode, float flow_scale, int world, int rank,
                       int reach, const void *nccl_id128, ofb_strips **out);

@@ -333,3 +333,38 @@ def test_native_strips_peer_memory_pair_replays_as_cuda_graph(ctx, oracle):
         torch.cuda.synchronize()
         for ns in ranks:
             ns.close()
+
+
+def test_native_strip_plan_matches_python_plan():
+    """The schedule exists twice -- StripPlan here (Python runner, gloo tests) and in csrc/strips.cu (native runner):
+    own rows, kernel rows and coarse-flow rows must agree for every rank and level; the native image buffers may
+    only be larger (they also hold the rows from which the coarser levels' halo rows are rebuilt locally)."""
+    import ctypes as C
+
+    from cuda_optical_flow_2_b200 import _lib
+    from cuda_optical_flow_2_b200.dist import StripPlan
+
+    lib = _lib.load()
+    out = (C.c_int * 8)()
+    n = 0
+    for (W, H, levels, win, reach) in [(7680, 4320, 4, 9, 16), (1920, 1080, 3, 9, 16), (3840, 2160, 4, 15, 8), (322, 406, 2, 5, 16),
+                                       (640, 480, 1, 5, 4), (1001, 777, 3, 19, 2)]:
+        for world in (1, 2, 3, 4, 8):
+            if (H >> (levels - 1)) < world:
+                continue
+            plan = StripPlan(W, H, levels, win, world, reach)
+            plan.validate()
+            for rank in range(world):
+                for k in range(levels):
+                    _lib.check(lib.ofb_strips_plan_query(W, H, levels, win, world, rank, reach, k, out))
+                    y0, y1, by0, by1, cy0, cy1, eb0, eb1 = list(out)
+                    s = plan.level(k, rank)
+                    assert (y0, y1, by0, by1, cy0, cy1) == (s.y0, s.y1, s.by0, s.by1, s.cy0, s.cy1), (W, H, levels, win, world, rank, k)
+                    assert eb0 <= by0 and eb1 >= by1 and 0 <= eb0 and eb1 <= (H >> k)
+                    if k + 1 < levels:  # every buffer row of the next level can be built from this level's buffer
+                        _lib.check(lib.ofb_strips_plan_query(W, H, levels, win, world, rank, reach, k + 1, out))
+                        ceb0, ceb1 = out[6], out[7]
+                        assert eb0 <= max(0, 2 * ceb0 - 1) and eb1 >= min(H >> k, 2 * (ceb1 - 1) + 2)
+                    n += 1
+    assert n > 100
+    assert lib.ofb_strips_plan_query(640, 480, 3, 9, 500, 0, 16, 0, out) != 0  # more strips than coarsest rows
