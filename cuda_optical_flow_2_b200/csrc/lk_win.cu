@@ -15,7 +15,7 @@ int lk_make_image_map(CUtensorMap *tm, const uint8_t *base, int w, int h, int n,
 int lk_make_flow_map(CUtensorMap *tm, const float *base, int w, int h, int n, size_t pair_stride_vec, int box_w, int box_rows,
                      int *usable);
 
-template <int WIN, int MODE, bool CUMOUT>
+template <int WIN, int MODE, bool CUMOUT, bool FAST>
 static int launch_one(const LkLevelArgs &a, cudaStream_t stream, unsigned long long *launches)
 {
     using C = LkCfg<WIN>;
@@ -23,7 +23,7 @@ static int launch_one(const LkLevelArgs &a, cudaStream_t stream, unsigned long l
     int dev = 0;
     OFB_CUDA_TRY(cudaGetDevice(&dev));
     if (dev < 64 && !attr_set[dev]) {
-        OFB_CUDA_TRY(cudaFuncSetAttribute(lk_level_kernel<WIN, MODE, CUMOUT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        OFB_CUDA_TRY(cudaFuncSetAttribute(lk_level_kernel<WIN, MODE, CUMOUT, FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           C::SMEM_BYTES));
         attr_set[dev] = true;
     }
@@ -99,34 +99,44 @@ static int launch_one(const LkLevelArgs &a, cudaStream_t stream, unsigned long l
     p.cum_tma = cum_tma;
 
     dim3 grid((unsigned)strips, (unsigned)nby, (unsigned)a.n_pairs);
-    lk_level_kernel<WIN, MODE, CUMOUT><<<grid, LK_NT, C::SMEM_BYTES, stream>>>(tmP, tmQ, tmC, p);
+    lk_level_kernel<WIN, MODE, CUMOUT, FAST><<<grid, LK_NT, C::SMEM_BYTES, stream>>>(tmP, tmQ, tmC, p);
     OFB_CUDA_TRY(cudaGetLastError());
     if (launches) ++*launches;
     return OFB_OK;
 }
 
-template <int WIN> int launch_lk_win(const LkLevelArgs &a, cudaStream_t s, unsigned long long *l)
+template <int WIN, bool FAST> static int launch_lk_win_solve(const LkLevelArgs &a, cudaStream_t s, unsigned long long *l)
 {
     const bool co = a.cum_out != nullptr;
-    if (a.cum_in == nullptr) return co ? launch_one<WIN, 0, true>(a, s, l) : launch_one<WIN, 0, false>(a, s, l);
-    if (a.warp_mode == OFB_WARP_BILINEAR) return co ? launch_one<WIN, 2, true>(a, s, l) : launch_one<WIN, 2, false>(a, s, l);
-    return co ? launch_one<WIN, 1, true>(a, s, l) : launch_one<WIN, 1, false>(a, s, l);
+    if (a.cum_in == nullptr) return co ? launch_one<WIN, 0, true, FAST>(a, s, l) : launch_one<WIN, 0, false, FAST>(a, s, l);
+    if (a.warp_mode == OFB_WARP_BILINEAR)
+        return co ? launch_one<WIN, 2, true, FAST>(a, s, l) : launch_one<WIN, 2, false, FAST>(a, s, l);
+    return co ? launch_one<WIN, 1, true, FAST>(a, s, l) : launch_one<WIN, 1, false, FAST>(a, s, l);
+}
+template <int WIN> int launch_lk_win(const LkLevelArgs &a, cudaStream_t s, unsigned long long *l)
+{
+    return a.solve_fast ? launch_lk_win_solve<WIN, true>(a, s, l) : launch_lk_win_solve<WIN, false>(a, s, l);
 }
 
 template int launch_lk_win<LK_WIN>(const LkLevelArgs &a, cudaStream_t s, unsigned long long *l);
 
 // Loads every variant of this window's kernel now (CUDA loads kernels lazily, and loading may synchronise the context:
 // a launch that first has to load its kernel can then not be enqueued behind a kernel that spins on a neighbour).
-template <int WIN> int preload_lk_win()
+template <int WIN, bool FAST> static int preload_lk_win_solve()
 {
     cudaFuncAttributes fa;
-    OFB_CUDA_TRY(cudaFuncGetAttributes(&fa, lk_level_kernel<WIN, 0, false>));
-    OFB_CUDA_TRY(cudaFuncGetAttributes(&fa, lk_level_kernel<WIN, 0, true>));
-    OFB_CUDA_TRY(cudaFuncGetAttributes(&fa, lk_level_kernel<WIN, 1, false>));
-    OFB_CUDA_TRY(cudaFuncGetAttributes(&fa, lk_level_kernel<WIN, 1, true>));
-    OFB_CUDA_TRY(cudaFuncGetAttributes(&fa, lk_level_kernel<WIN, 2, false>));
-    OFB_CUDA_TRY(cudaFuncGetAttributes(&fa, lk_level_kernel<WIN, 2, true>));
+    OFB_CUDA_TRY(cudaFuncGetAttributes(&fa, lk_level_kernel<WIN, 0, false, FAST>));
+    OFB_CUDA_TRY(cudaFuncGetAttributes(&fa, lk_level_kernel<WIN, 0, true, FAST>));
+    OFB_CUDA_TRY(cudaFuncGetAttributes(&fa, lk_level_kernel<WIN, 1, false, FAST>));
+    OFB_CUDA_TRY(cudaFuncGetAttributes(&fa, lk_level_kernel<WIN, 1, true, FAST>));
+    OFB_CUDA_TRY(cudaFuncGetAttributes(&fa, lk_level_kernel<WIN, 2, false, FAST>));
+    OFB_CUDA_TRY(cudaFuncGetAttributes(&fa, lk_level_kernel<WIN, 2, true, FAST>));
     return OFB_OK;
+}
+template <int WIN> int preload_lk_win()
+{
+    const int rc = preload_lk_win_solve<WIN, false>();
+    return rc ? rc : preload_lk_win_solve<WIN, true>();
 }
 template int preload_lk_win<LK_WIN>();
 

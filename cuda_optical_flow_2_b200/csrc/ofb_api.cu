@@ -31,6 +31,7 @@ static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; 
 struct ofb_ctx {
     int device = 0;
     int sm_count = 0;
+    int solve_fast = 0; // OFB_SOLVE_*: which 2x2 solve the fused level kernel runs (ofb_ctx_set_solve)
     cudaStream_t stream = nullptr; // used by the synchronous host-pointer entry points
     cudaStream_t lane_stream[OFB_LANES] = {}; // the batched host entry point pipelines sub-batches over these
     uint8_t *ws = nullptr;
@@ -52,6 +53,7 @@ namespace ofb {
 // accessors for the other translation units (strips.cu): ofb_ctx stays private to this file
 int ctx_device(const ofb_ctx *c) { return c->device; }
 int ctx_sm_count(const ofb_ctx *c) { return c->sm_count; }
+int ctx_solve_fast(const ofb_ctx *c) { return c->solve_fast; }
 unsigned long long *ctx_launch_counter(ofb_ctx *c) { return &c->launches; }
 
 struct DeviceGuard {
@@ -235,6 +237,7 @@ static int run_pairs_device(ofb_ctx *c, const ofb_params *p, const PairPlan &pl,
         a.flow_out = flow_levels[k];
         a.flow_pair_stride = (size_t)pl.w[k] * pl.h[k];
         a.sm_count = c->sm_count;
+    a.solve_fast = c->solve_fast;
         if (k < L - 1) {
             // cum_{k+1}: the coarsest level's cumulative flow is its residual flow
             a.cum_in = (k + 1 == L - 1) ? flow_levels[k + 1] : reinterpret_cast<const float *>(base + pl.off_cum[k + 1]);
@@ -361,6 +364,24 @@ int ofb_ctx_sm_count(const ofb_ctx *c, int *sm_count)
 {
     OFB_CHECK_CTX(c);
     if (sm_count) *sm_count = c->sm_count;
+    return OFB_OK;
+}
+
+int ofb_ctx_set_solve(ofb_ctx *c, int solve_mode)
+{
+    OFB_CHECK_CTX(c);
+    if (solve_mode != OFB_SOLVE_EXACT && solve_mode != OFB_SOLVE_FAST) {
+        set_error("unknown solve mode %d", solve_mode);
+        return OFB_ERR_INVALID;
+    }
+    c->solve_fast = solve_mode == OFB_SOLVE_FAST;
+    return OFB_OK;
+}
+
+int ofb_ctx_get_solve(const ofb_ctx *c, int *solve_mode)
+{
+    OFB_CHECK_CTX(c);
+    if (solve_mode) *solve_mode = c->solve_fast ? OFB_SOLVE_FAST : OFB_SOLVE_EXACT;
     return OFB_OK;
 }
 
@@ -518,6 +539,7 @@ int ofb_lk_level_device(ofb_ctx *c, const uint8_t *prev_d, const uint8_t *next_d
     a.cum_out = cum_out_d;
     a.flow_pair_stride = (size_t)w * h;
     a.sm_count = c->sm_count;
+    a.solve_fast = c->solve_fast;
     if (cum_in_d && ((w >> 1) < 1 || (h >> 1) < 1)) {
         set_error("level %dx%d has no coarser level", w, h);
         return OFB_ERR_INVALID;
@@ -570,6 +592,7 @@ int ofb_lk_level_strip_device(ofb_ctx *c, const uint8_t *prev_d, const uint8_t *
     a.flow_pair_stride = 0;
     a.reach_overflow = reach_overflow_d;
     a.sm_count = c->sm_count;
+    a.solve_fast = c->solve_fast;
     return launch_lk_level(a, static_cast<cudaStream_t>(stream), &c->launches);
 }
 
@@ -697,6 +720,7 @@ int ofb_calc_opt_flow_host_u8c3(ofb_ctx *c, const unsigned char *prev, const uns
     a.cum_h_local = h >> 1;
     a.flow_out = reinterpret_cast<float *>(B + off_flow);
     a.sm_count = c->sm_count;
+    a.solve_fast = c->solve_fast;
     rc = launch_lk_level(a, st, &c->launches);
     if (rc) return rc;
     OFB_CUDA_TRY(cudaMemcpyAsync(optFlowPyramid[level], B + off_flow, (size_t)w * h * 8, cudaMemcpyDeviceToHost, st));
@@ -1231,6 +1255,7 @@ int ofb_stream_push_bgr_host(ofb_stream *s, const unsigned char *frame_bgr, floa
             a.flow_scale = p.flow_scale;
             a.flow_out = reinterpret_cast<float *>(B + s->off_flow[k]);
             a.sm_count = c->sm_count;
+    a.solve_fast = c->solve_fast;
             if (k < p.levels - 1) {
                 a.cum_in = reinterpret_cast<const float *>(k + 1 == p.levels - 1 ? B + s->off_flow[k + 1] : B + s->off_cum[k + 1]);
                 a.cum_w = p.w >> (k + 1);

@@ -45,6 +45,7 @@ struct LkLevelArgs {
     size_t flow_pair_stride;  // float2 elements between pairs (flow_out and cum_out)
     int *reach_overflow;   // optional device flag: a warp sample fell outside the local rows
     int sm_count;
+    int solve_fast;        // OFB_SOLVE_FAST: tolerance-mode solve (lk_solve4_fast) instead of the bit-exact one
 };
 int launch_lk_level(const LkLevelArgs &a, cudaStream_t stream, unsigned long long *launches);
 int preload_lk_level(int win); // loads the window's kernels now instead of at their first launch

@@ -31,6 +31,7 @@ namespace ofb {
 // accessors implemented in ofb_api.cu (ofb_ctx is private to it)
 int ctx_device(const ofb_ctx *c);
 int ctx_sm_count(const ofb_ctx *c);
+int ctx_solve_fast(const ofb_ctx *c);
 unsigned long long *ctx_launch_counter(ofb_ctx *c);
 
 // ---- NCCL through dlopen ------------------------------------------------------------------------------------
@@ -873,6 +874,7 @@ int ofb_strips_run_device(ofb_strips *st, const uint8_t *prev_own_d, const uint8
         a.flow_pair_stride = 0;
         a.reach_overflow = st->overflow;
         a.sm_count = ctx_sm_count(st->ctx);
+        a.solve_fast = ctx_solve_fast(st->ctx);
         int rc = launch_lk_level(a, q, launches);
         if (rc) return rc;
     }

@@ -6,8 +6,9 @@ import re
 import subprocess
 import sys
 
-obj, win, mode, co = sys.argv[1], sys.argv[2], sys.argv[3], sys.argv[4]
-fun = f"_ZN3ofb15lk_level_kernelILi{win}ELi{mode}ELb{co}EEEv14CUtensorMap_stS1_S1_NS_14LkKernelParamsE"
+obj, win, mode, co = sys.argv[1:5]
+fast = sys.argv[5] if len(sys.argv) > 5 else "0"
+fun = f"_ZN3ofb15lk_level_kernelILi{win}ELi{mode}ELb{co}ELb{fast}EEEv14CUtensorMap_stS1_S1_NS_14LkKernelParamsE"
 out = subprocess.run(["cuobjdump", "-sass", "-fun", fun, obj], capture_output=True, text=True).stdout
 ins = []
 for line in out.splitlines():
