@@ -16,6 +16,7 @@ LIB_PATH = os.environ.get("OFB200_LIB") or os.path.join(_HERE, "libofb200.so")
 
 OFB_OK, OFB_ERR_INVALID, OFB_ERR_CUDA, OFB_ERR_UNSUPPORTED, OFB_ERR_NOMEM = 0, 1, 2, 3, 4
 WARP_AS_WRITTEN, WARP_NEAREST, WARP_BILINEAR = 0, 1, 2
+SOLVE_EXACT, SOLVE_FAST = 0, 1
 MAX_LEVELS, MAX_WINDOW = 8, 19
 PROFILE_PYRAMID = 100
 
@@ -45,6 +46,8 @@ SIGNATURES = {
     "ofb_ctx_destroy": (C.c_int, [_vp]),
     "ofb_ctx_device": (C.c_int, [_vp, i32p]),
     "ofb_ctx_sm_count": (C.c_int, [_vp, i32p]),
+    "ofb_ctx_set_solve": (C.c_int, [_vp, C.c_int]),
+    "ofb_ctx_get_solve": (C.c_int, [_vp, i32p]),
     "ofb_ctx_launch_count": (C.c_int, [_vp, C.POINTER(C.c_ulonglong)]),
     "ofb_ctx_profile_enable": (C.c_int, [_vp, C.c_int]),
     "ofb_ctx_profile_read": (C.c_int, [_vp, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_ulonglong)]),

@@ -18,7 +18,7 @@ from typing import Optional, Sequence
 import numpy as np
 
 from . import _lib as L
-from ._lib import WARP_AS_WRITTEN, WARP_BILINEAR, WARP_NEAREST, OfbError, OfbParams  # noqa: F401
+from ._lib import SOLVE_EXACT, SOLVE_FAST, WARP_AS_WRITTEN, WARP_BILINEAR, WARP_NEAREST, OfbError, OfbParams  # noqa: F401
 
 REFERENCE_WINDOW = 19  # OptFlowGpu.cu:1944-1945
 
@@ -81,6 +81,18 @@ class Context:
         v = C.c_ulonglong()
         L.check(self._lib.ofb_ctx_launch_count(self._h, C.byref(v)))
         return v.value
+
+    @property
+    def solve(self) -> int:
+        """SOLVE_EXACT (default; the reference's double-precision operation order, bit-identical flow) or SOLVE_FAST
+        (exact 64-bit integer determinant and numerators, one float reciprocal; |d| <= 1e-4 px + 1e-5 |ref| per level)."""
+        v = C.c_int()
+        L.check(self._lib.ofb_ctx_get_solve(self._h, C.byref(v)))
+        return v.value
+
+    @solve.setter
+    def solve(self, mode: int) -> None:
+        L.check(self._lib.ofb_ctx_set_solve(self._h, int(mode)))
 
     def profile_enable(self, on: bool = True) -> None:
         """CUDA-event timing around each fused-LK launch (tag = level) and the pyramid build."""

@@ -24,7 +24,7 @@ static int launch_one(const LkLevelArgs &a, cudaStream_t stream, unsigned long l
     OFB_CUDA_TRY(cudaGetDevice(&dev));
     if (dev < 64 && !attr_set[dev]) {
         OFB_CUDA_TRY(cudaFuncSetAttribute(lk_level_kernel<WIN, MODE, CUMOUT, FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          C::SMEM_BYTES));
+                                          C::smem_bytes(FAST, CUMOUT && MODE != 0)));
         attr_set[dev] = true;
     }
     CUtensorMap tmP, tmQ;
@@ -99,7 +99,7 @@ static int launch_one(const LkLevelArgs &a, cudaStream_t stream, unsigned long l
     p.cum_tma = cum_tma;
 
     dim3 grid((unsigned)strips, (unsigned)nby, (unsigned)a.n_pairs);
-    lk_level_kernel<WIN, MODE, CUMOUT, FAST><<<grid, LK_NT, C::SMEM_BYTES, stream>>>(tmP, tmQ, tmC, p);
+    lk_level_kernel<WIN, MODE, CUMOUT, FAST><<<grid, LK_NT, C::smem_bytes(FAST, CUMOUT && MODE != 0), stream>>>(tmP, tmQ, tmC, p);
     OFB_CUDA_TRY(cudaGetLastError());
     if (launches) ++*launches;
     return OFB_OK;

@@ -344,3 +344,107 @@ def test_bad_arguments_are_rejected(ctx):
     bad = torch.zeros((1, 64, 72), dtype=torch.uint8, device="cuda")
     with pytest.raises(OfbError):
         ctx.flow_pairs_device(bad, bad, 64, 1, 9)  # pitch not a multiple of 16
+
+
+# ------------------------------------------------------------------------------------ tolerance-mode solve (OFB_SOLVE_FAST)
+def assert_flow_within_tolerance(got: np.ndarray, ref: np.ndarray, what: str = "", ulps: bool = True):
+    """The stated bar of the tolerance-mode solve, per level on identical inputs: non-finite values on exactly the same
+    pixels, and |du|, |dv| <= TOL_ABS + TOL_REL * |ref| everywhere else."""
+    fg, fr = np.isfinite(got), np.isfinite(ref)
+    assert np.array_equal(fg, fr), f"{what}: finite masks differ at {np.argwhere(fg != fr)[:5]}"
+    d = np.abs(got[fg].astype(np.float64) - ref[fg])
+    lim = TOL_ABS + TOL_REL * np.abs(ref[fg])
+    assert (d <= lim).all(), f"{what}: max abs diff {d.max():.3e} exceeds tolerance"
+    # and in fact a few float ulps: exact integer determinant / numerators, one rounding each, 1-ulp reciprocal
+    rel = d / np.maximum(np.abs(ref[fg]), 1e-30)
+    big = np.abs(ref[fg]) > 1e-3
+    if ulps and big.any():  # (not for sums like the cumulative flow, where terms cancel)
+        assert rel[big].max() < 1e-6, f"{what}: relative error {rel[big].max():.3e}"
+
+
+@pytest.fixture
+def fast_ctx(ctx):
+    from cuda_optical_flow_2_b200 import SOLVE_EXACT, SOLVE_FAST
+
+    assert ctx.solve == SOLVE_EXACT
+    ctx.solve = SOLVE_FAST
+    yield ctx
+    ctx.solve = SOLVE_EXACT
+
+
+@pytest.mark.parametrize("w,h,win", [(640, 480, 5), (640, 480, 9), (320, 240, 19), (203, 117, 15), (64, 64, 3),
+                                     (131, 59, 7), (250, 40, 11), (96, 200, 13), (128, 128, 17), (1920, 1080, 9)])
+def test_fast_solve_coarsest_level_within_tolerance(fast_ctx, oracle, w, h, win):
+    torch = _torch()
+    from cuda_optical_flow_2_b200 import planar_to_device
+
+    prev, nxt = frames(oracle, w, h)
+    flow = fast_ctx.lk_level_device(planar_to_device(prev[None]), planar_to_device(nxt[None]), w, win, cum_in=None)
+    torch.cuda.synchronize()
+    ref = oracle.lk_level(prev, nxt, win, oracle.SUMS_EXACT)
+    assert_flow_within_tolerance(flow.cpu().numpy()[0], ref, f"{w}x{h} win {win}")
+
+
+def test_fast_solve_flat_areas_same_nonfinite_pixels(fast_ctx, oracle):
+    torch = _torch()
+    from cuda_optical_flow_2_b200 import planar_to_device
+
+    w, h = 160, 96
+    prev, nxt = frames(oracle, w, h)
+    prev[20:70, 30:120] = 77
+    nxt[20:70, 30:120] = 77
+    flow = fast_ctx.lk_level_device(planar_to_device(prev[None]), planar_to_device(nxt[None]), w, 9)
+    torch.cuda.synchronize()
+    ref = oracle.lk_level(prev, nxt, 9, oracle.SUMS_EXACT)
+    assert (~np.isfinite(ref)).sum() > 100
+    assert_flow_within_tolerance(flow.cpu().numpy()[0], ref)
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2])
+@pytest.mark.parametrize("w,h,levels,win", [(640, 480, 4, 9), (322, 246, 3, 5), (1920, 1080, 3, 9), (400, 300, 3, 15)])
+def test_fast_solve_every_level_on_identical_inputs(ctx, oracle, mode, w, h, levels, win):
+    """Per level, on the EXACT pipeline's inputs (pyramid level + coarser cumulative flow): the tolerance-mode
+    kernel against the oracle's residual flow and cumulative flow of that level."""
+    torch = _torch()
+    from cuda_optical_flow_2_b200 import SOLVE_EXACT, SOLVE_FAST, planar_to_device
+
+    prev = oracle.make_frame(w, h, 0, 0, 8, 777)
+    nxt = oracle.make_frame(w, h, 3.25, -1.75, 8, 777)
+    ref, cums = oracle.flow_pair(prev, nxt, levels, win, mode, oracle.SUMS_EXACT, 1.0, want_cum=True)
+    pp, pn = oracle.gauss_pyramid(prev, levels), oracle.gauss_pyramid(nxt, levels)
+    ctx.solve = SOLVE_FAST
+    try:
+        for k in range(levels - 1, -1, -1):
+            cum_in = None if k == levels - 1 else torch.from_numpy(cums[k + 1][None].copy()).cuda()
+            cum_out = torch.empty((1, h >> k, w >> k, 2), dtype=torch.float32, device="cuda")
+            flow = ctx.lk_level_device(planar_to_device(pp[k][None]), planar_to_device(pn[k][None]), w >> k, win,
+                                       cum_in=cum_in, warp_mode=mode, cum_out=cum_out)
+            torch.cuda.synchronize()
+            assert_flow_within_tolerance(flow.cpu().numpy()[0], ref[k], f"mode {mode} level {k}")
+            assert_flow_within_tolerance(cum_out.cpu().numpy()[0], cums[k], f"mode {mode} level {k} cumulative", ulps=False)
+    finally:
+        ctx.solve = SOLVE_EXACT
+
+
+def test_fast_solve_whole_pipeline_close_to_exact(fast_ctx, oracle):
+    """Through all levels the two modes can part at warped levels (a last-ulp difference of the coarser flow can flip
+    its rounding to 1/256 px and so one bilinear weight); report and bound that: almost everywhere inside the
+    per-level tolerance, and never by more than a few hundredths of a pixel."""
+    torch = _torch()
+    from cuda_optical_flow_2_b200 import planar_to_device
+
+    w, h, levels, win = 1920, 1080, 3, 9
+    prev = oracle.make_frame(w, h, 0, 0, 8, 31)
+    nxt = oracle.make_frame(w, h, 2.5, -1.25, 8, 31)
+    total = torch.empty((1, h, w, 2), dtype=torch.float32, device="cuda")
+    fast_ctx.flow_pairs_device(planar_to_device(prev[None]), planar_to_device(nxt[None]), w, levels, win, total_flow=total)
+    torch.cuda.synchronize()
+    _, cums = oracle.flow_pair(prev, nxt, levels, win, 2, oracle.SUMS_EXACT, 1.0, want_cum=True)
+    got, ref = total.cpu().numpy()[0], cums[0]
+    assert np.array_equal(np.isfinite(got), np.isfinite(ref))
+    fin = np.isfinite(ref)
+    d = np.abs(got[fin] - ref[fin])
+    lim = TOL_ABS + TOL_REL * np.abs(ref[fin])
+    assert (d > lim).mean() < 1e-3, f"{(d > lim).mean():.2e} of the total-flow values beyond the per-level tolerance"
+    well = np.abs(ref[fin]) < 100.0  # ill-conditioned windows amplify any input change without bound
+    assert d[well].max() < 0.25, f"max |d| {d[well].max():.3e}"
