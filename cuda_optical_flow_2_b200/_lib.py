@@ -46,6 +46,7 @@ SIGNATURES = {
     "ofb_ctx_destroy": (C.c_int, [_vp]),
     "ofb_ctx_device": (C.c_int, [_vp, i32p]),
     "ofb_ctx_sm_count": (C.c_int, [_vp, i32p]),
+    "ofb_ctx_reserve_pairs": (C.c_int, [_vp, C.POINTER(OfbParams)]),
     "ofb_ctx_set_solve": (C.c_int, [_vp, C.c_int]),
     "ofb_ctx_get_solve": (C.c_int, [_vp, i32p]),
     "ofb_ctx_launch_count": (C.c_int, [_vp, C.POINTER(C.c_ulonglong)]),
@@ -67,6 +68,7 @@ SIGNATURES = {
     "ofb_inverse_matrix_f32_host": (C.c_int, [_vp, f32p, f32p, f32p, f32p, f32p, C.POINTER(f32p), C.c_int, C.c_int,
                                               C.c_int]),
     "ofb_flow_pairs_host": (C.c_int, [_vp, C.POINTER(OfbParams), u8p, u8p, C.c_int, C.POINTER(f32p)]),
+    "ofb_flow_pairs_host_ex": (C.c_int, [_vp, C.POINTER(OfbParams), u8p, u8p, C.c_int, C.POINTER(f32p), f32p]),
     "ofb_grayscale_avg_host_u8c3": (C.c_int, [_vp, u8p, u8p, C.c_int, C.c_int]),
     "ofb_bilinear_filter_host_u8c3": (C.c_int, [_vp, u8p, u8p, u8p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double,
                                                 C.c_double]),
@@ -81,6 +83,7 @@ SIGNATURES = {
                                     _vp, C.POINTER(_vp)]),
     "ofb_strips_own_rows": (C.c_int, [_vp, C.c_int, i32p, i32p]),
     "ofb_strips_run_device": (C.c_int, [_vp, _vp, _vp, _sz, _vp]),
+    "ofb_strips_run_phase_device": (C.c_int, [_vp, _vp, _vp, _sz, C.c_int, _vp]),
     "ofb_strips_result": (C.c_int, [_vp, C.c_int, C.POINTER(_vp), C.POINTER(_vp)]),
     "ofb_strips_check": (C.c_int, [_vp, _vp, i32p]),
     "ofb_strips_destroy": (C.c_int, [_vp]),

@@ -94,6 +94,12 @@ class Context:
     def solve(self, mode: int) -> None:
         L.check(self._lib.ofb_ctx_set_solve(self._h, int(mode)))
 
+    def reserve_pairs(self, w: int, h: int, levels: int, win: int, n_pairs: int) -> None:
+        """Size the context workspace for flow_pairs_device calls of this shape now (a later growth would invalidate
+        CUDA graphs captured from earlier calls)."""
+        p = OfbParams(w, h, levels, win, WARP_BILINEAR, 1.0, n_pairs)
+        L.check(self._lib.ofb_ctx_reserve_pairs(self._h, C.byref(p)))
+
     def profile_enable(self, on: bool = True) -> None:
         """CUDA-event timing around each fused-LK launch (tag = level) and the pyramid build."""
         L.check(self._lib.ofb_ctx_profile_enable(self._h, 1 if on else 0))
@@ -193,13 +199,19 @@ class Context:
     def flow_arrows(self, flow_pyramid: Sequence[np.ndarray], w: int, h: int, levels: int, level: int, arrow_res: int) -> np.ndarray:
         """(n, 4) int32 array of (x0, y0, x1, y1): the arrows main.cu:125-171 draws."""
         flows = [_f32(f) for f in flow_pyramid]
-        cap = (arrow_res + 2) * ((h >> level) // max((w >> level) // arrow_res, 1) + 2)
+        # one arrow per grid point at most: the grid step is (w >> level) // arrow_res in both directions (main.cu:125-133)
+        step = max((w >> level) // max(arrow_res, 1), 1)
+        cap = -(-(w >> level) // step) * -(-(h >> level) // step)
         buf = np.empty((cap, 4), np.int32)
         n = C.c_int(0)
         L.check(self._lib.ofb_flow_arrows_host(self._h, _ptrs(flows, L.f32p), w, h, levels, level, arrow_res,
                                                buf.ctypes.data_as(L.i32p), cap, C.byref(n)))
-        assert n.value <= cap
-        return buf[: n.value].copy()
+        if n.value > cap:  # (the C side reports the full count and truncates the list: ask again with room for all)
+            cap = n.value
+            buf = np.empty((cap, 4), np.int32)
+            L.check(self._lib.ofb_flow_arrows_host(self._h, _ptrs(flows, L.f32p), w, h, levels, level, arrow_res,
+                                                   buf.ctypes.data_as(L.i32p), cap, C.byref(n)))
+        return buf[: min(n.value, cap)].copy()
 
     def grayscale_avg(self, src: np.ndarray, h: int, w: int) -> np.ndarray:
         """gpu::grayscale_avg(src, dest, h, w) (OptFlowGpu.cu:75; height before width like the reference)."""
@@ -264,6 +276,29 @@ class Context:
         L.check(self._lib.ofb_flow_pairs_host(self._h, C.byref(p), _u8(prev).ctypes.data_as(L.u8p),
                                               _u8(next).ctypes.data_as(L.u8p), channels, ptrs))
         return list(out)
+
+    def total_flow_pairs_host(self, prev: np.ndarray, next: np.ndarray, levels: int, win: int,
+                              warp_mode: int = WARP_BILINEAR, flow_scale: float = 1.0,
+                              out: Optional[np.ndarray] = None) -> np.ndarray:
+        """As flow_pairs_host, but only the level-0 composition of main.cu:136-147 (the total flow, (n, h, w, 2))
+        leaves the device: 8 bytes per pixel over PCIe instead of 10.5."""
+        if prev.ndim == 4:
+            if prev.shape[3] != 3:
+                raise ValueError("4-d input must be (n, h, w, 3)")
+            channels, (n, h, w) = 3, prev.shape[:3]
+        elif prev.ndim == 3:
+            channels, (n, h, w) = 1, prev.shape
+        else:
+            raise ValueError("prev must be (n,h,w) or (n,h,w,3)")
+        if next.shape != prev.shape:
+            raise ValueError("prev and next differ in shape")
+        p = OfbParams(w, h, levels, win, warp_mode, flow_scale, n)
+        if out is None:
+            out = np.empty((n, h, w, 2), np.float32)
+        L.check(self._lib.ofb_flow_pairs_host_ex(self._h, C.byref(p), _u8(prev).ctypes.data_as(L.u8p),
+                                                 _u8(next).ctypes.data_as(L.u8p), channels, None,
+                                                 _f32(out).ctypes.data_as(L.f32p)))
+        return out
 
     # ---------------------------------------------------------------- device-resident API
     def flow_pairs_device(self, prev, next, w: int, levels: int, win: int, warp_mode: int = WARP_BILINEAR,

@@ -36,6 +36,11 @@ struct ofb_ctx {
     cudaStream_t lane_stream[OFB_LANES] = {}; // the batched host entry point pipelines sub-batches over these
     uint8_t *ws = nullptr;
     size_t ws_bytes = 0;
+    // The workspace serves ONE stream at a time: every asynchronous use records ws_event on its stream, and a later user
+    // on another stream waits for it first (ws_acquire / ws_release).
+    cudaEvent_t ws_event = nullptr;
+    cudaStream_t ws_stream = nullptr;
+    bool ws_busy = false;
     unsigned long long launches = 0;
     // optional in-situ timing: CUDA events around each fused-LK launch (tag = level) and around the
     // pyramid build (tag = OFB_PROFILE_PYRAMID), recorded on the stream the work is launched on
@@ -56,28 +61,8 @@ int ctx_sm_count(const ofb_ctx *c) { return c->sm_count; }
 int ctx_solve_fast(const ofb_ctx *c) { return c->solve_fast; }
 unsigned long long *ctx_launch_counter(ofb_ctx *c) { return &c->launches; }
 
-struct DeviceGuard {
-    int prev = -1;
-    bool ok = false;
-    explicit DeviceGuard(int dev)
-    {
-        if (cudaGetDevice(&prev) != cudaSuccess) {
-            prev = -1;
-            set_error("no usable CUDA device: %s", cudaGetErrorString(cudaGetLastError()));
-            return;
-        }
-        if (prev != dev && cudaSetDevice(dev) != cudaSuccess) {
-            set_error("cudaSetDevice(%d) failed: %s", dev, cudaGetErrorString(cudaGetLastError()));
-            return;
-        }
-        ok = true;
-    }
-    ~DeviceGuard()
-    {
-        if (prev >= 0) cudaSetDevice(prev);
-    }
-};
-
+// Growing frees the old block after a device synchronisation: CUDA graphs captured from earlier calls hold pointers
+// into it and must be re-captured (ofb_ctx_reserve_pairs sizes the workspace up front so that this never happens).
 static int ws_reserve(ofb_ctx *c, size_t bytes)
 {
     if (bytes <= c->ws_bytes) return OFB_OK;
@@ -95,6 +80,20 @@ static int ws_reserve(ofb_ctx *c, size_t bytes)
         return OFB_ERR_NOMEM;
     }
     c->ws_bytes = want;
+    return OFB_OK;
+}
+
+// Orders the uses of the shared workspace across streams (see ofb_ctx::ws_event).
+static int ws_acquire(ofb_ctx *c, cudaStream_t st)
+{
+    if (c->ws_busy && c->ws_stream != st) OFB_CUDA_TRY(cudaStreamWaitEvent(st, c->ws_event, 0));
+    return OFB_OK;
+}
+static int ws_release(ofb_ctx *c, cudaStream_t st)
+{
+    OFB_CUDA_TRY(cudaEventRecord(c->ws_event, st));
+    c->ws_stream = st;
+    c->ws_busy = true;
     return OFB_OK;
 }
 
@@ -237,7 +236,7 @@ static int run_pairs_device(ofb_ctx *c, const ofb_params *p, const PairPlan &pl,
         a.flow_out = flow_levels[k];
         a.flow_pair_stride = (size_t)pl.w[k] * pl.h[k];
         a.sm_count = c->sm_count;
-    a.solve_fast = c->solve_fast;
+        a.solve_fast = c->solve_fast;
         if (k < L - 1) {
             // cum_{k+1}: the coarsest level's cumulative flow is its residual flow
             a.cum_in = (k + 1 == L - 1) ? flow_levels[k + 1] : reinterpret_cast<const float *>(base + pl.off_cum[k + 1]);
@@ -319,6 +318,13 @@ int ofb_ctx_create(int device, ofb_ctx **out)
         delete c;
         return OFB_ERR_CUDA;
     }
+    e = cudaEventCreateWithFlags(&c->ws_event, cudaEventDisableTiming);
+    if (e != cudaSuccess) {
+        set_error("cudaEventCreate failed: %s", cudaGetErrorString(e));
+        cudaStreamDestroy(c->stream);
+        delete c;
+        return OFB_ERR_CUDA;
+    }
     for (int l = 0; l < OFB_LANES; l++) {
         e = cudaStreamCreateWithFlags(&c->lane_stream[l], cudaStreamNonBlocking);
         if (e != cudaSuccess) {
@@ -344,6 +350,7 @@ int ofb_ctx_destroy(ofb_ctx *c)
             }
             if (c->ws) cudaFree(c->ws);
             if (c->bil_lut) cudaFree(c->bil_lut);
+            if (c->ws_event) cudaEventDestroy(c->ws_event);
             if (c->stream) cudaStreamDestroy(c->stream);
             for (int l = 0; l < OFB_LANES; l++)
                 if (c->lane_stream[l]) cudaStreamDestroy(c->lane_stream[l]);
@@ -474,8 +481,23 @@ int ofb_flow_pairs_device(ofb_ctx *c, const ofb_params *p, const uint8_t *prev_d
     plan_pairs(p, &pl, &cv);
     rc = ws_reserve(c, pl.bytes);
     if (rc) return rc;
-    return run_pairs_device(c, p, pl, c->ws, prev_d, next_d, pitch_bytes, image_stride_bytes, flow_levels_d, total_flow_d,
-                            static_cast<cudaStream_t>(stream));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if ((rc = ws_acquire(c, st))) return rc;
+    rc = run_pairs_device(c, p, pl, c->ws, prev_d, next_d, pitch_bytes, image_stride_bytes, flow_levels_d, total_flow_d, st);
+    if (rc) return rc;
+    return ws_release(c, st);
+}
+
+int ofb_ctx_reserve_pairs(ofb_ctx *c, const ofb_params *p)
+{
+    OFB_CHECK_CTX(c);
+    int rc = check_params(p);
+    if (rc) return rc;
+    OFB_GUARD(c);
+    Carver cv;
+    PairPlan pl;
+    plan_pairs(p, &pl, &cv);
+    return ws_reserve(c, pl.bytes);
 }
 
 int ofb_pyr_down_device(ofb_ctx *c, const uint8_t *src_d, size_t src_pitch, size_t src_image_stride, int sw, int sh,
@@ -633,6 +655,7 @@ int ofb_gauss_pyramid_host_u8c3(ofb_ctx *c, unsigned char **pyramid, int w, int 
     int rc = ws_reserve(c, cv.off);
     if (rc) return rc;
     cudaStream_t st = c->stream;
+    if ((rc = ws_acquire(c, st))) return rc;
     OFB_CUDA_TRY(cudaMemcpyAsync(c->ws + off[0], pyramid[0], (size_t)w * h * 3, cudaMemcpyHostToDevice, st));
     for (int k = 1; k < levels; k++) {
         const int sw = w >> (k - 1), sh = h >> (k - 1), dw = w >> k, dh = h >> k;
@@ -679,6 +702,7 @@ int ofb_calc_opt_flow_host_u8c3(ofb_ctx *c, const unsigned char *prev, const uns
     int rc = ws_reserve(c, cv.off);
     if (rc) return rc;
     cudaStream_t st = c->stream;
+    if ((rc = ws_acquire(c, st))) return rc;
     uint8_t *B = c->ws;
     const size_t c3 = (size_t)w * h * 3;
     OFB_CUDA_TRY(cudaMemcpyAsync(B + off_c3, prev, c3, cudaMemcpyHostToDevice, st));
@@ -742,6 +766,7 @@ int ofb_conv_3ch_1ch_u8_f32_host(ofb_ctx *c, const unsigned char *src_h, int w, 
     int rc = ws_reserve(c, cv.off);
     if (rc) return rc;
     cudaStream_t st = c->stream;
+    if ((rc = ws_acquire(c, st))) return rc;
     OFB_CUDA_TRY(cudaMemcpyAsync(c->ws + off_s, src_h, (size_t)w * h * 3, cudaMemcpyHostToDevice, st));
     rc = launch_conv_c3_f32(c->ws + off_s, w, h, reinterpret_cast<float *>(c->ws + off_d), mask, mw, mh, st, &c->launches);
     if (rc) return rc;
@@ -765,6 +790,7 @@ int ofb_srm_1ch_f32_host(ofb_ctx *c, const float *arr1_h, const float *arr2_h, i
     int rc = ws_reserve(c, cv.off);
     if (rc) return rc;
     cudaStream_t st = c->stream;
+    if ((rc = ws_acquire(c, st))) return rc;
     OFB_CUDA_TRY(cudaMemcpyAsync(c->ws + oa, arr1_h, n, cudaMemcpyHostToDevice, st));
     const float *bdev = reinterpret_cast<const float *>(c->ws + oa);
     if (arr2_h != arr1_h) {
@@ -797,6 +823,7 @@ int ofb_inverse_matrix_f32_host(ofb_ctx *c, const float *sumIx2, const float *su
     int rc = ws_reserve(c, cv.off);
     if (rc) return rc;
     cudaStream_t st = c->stream;
+    if ((rc = ws_acquire(c, st))) return rc;
     const float *src[5] = {sumIx2, sumIy2, sumIxIy, sumIxIt, sumIyIt};
     for (int k = 0; k < 5; k++) OFB_CUDA_TRY(cudaMemcpyAsync(c->ws + o[k], src[k], n, cudaMemcpyHostToDevice, st));
     rc = launch_inverse_f32(reinterpret_cast<const float *>(c->ws + o[0]), reinterpret_cast<const float *>(c->ws + o[1]),
@@ -809,21 +836,18 @@ int ofb_inverse_matrix_f32_host(ofb_ctx *c, const float *sumIx2, const float *su
     return OFB_OK;
 }
 
-int ofb_flow_pairs_host(ofb_ctx *c, const ofb_params *p, const unsigned char *prev_h, const unsigned char *next_h,
-                        int channels, float *const *flow_levels_h)
+// flow_levels_h: NULL, or an array whose NULL entries are levels the caller does not want downloaded; total_flow_h: NULL
+// or the level-0 composition (main.cu:136-147).  At least one output.
+static int flow_pairs_host_impl(ofb_ctx *c, const ofb_params *p, const unsigned char *prev_h, const unsigned char *next_h,
+                                int channels, float *const *flow_levels_h, float *total_flow_h)
 {
     OFB_CHECK_CTX(c);
     int rc = check_params(p);
     if (rc) return rc;
-    if (!prev_h || !next_h || !flow_levels_h || (channels != 1 && channels != 3)) {
+    if (!prev_h || !next_h || (!flow_levels_h && !total_flow_h) || (channels != 1 && channels != 3)) {
         set_error("flow_pairs_host: bad arguments (channels %d)", channels);
         return OFB_ERR_INVALID;
     }
-    for (int k = 0; k < p->levels; k++)
-        if (!flow_levels_h[k]) {
-            set_error("flow_levels_h[%d] is NULL", k);
-            return OFB_ERR_INVALID;
-        }
     OFB_GUARD(c);
     // Software pipeline over sub-batches on OFB_LANES streams: while one lane downloads its flow the
     // other uploads and computes, so the PCIe directions and the SMs overlap (with pinned host memory).
@@ -838,7 +862,7 @@ int ofb_flow_pairs_host(ofb_ctx *c, const ofb_params *p, const unsigned char *pr
     const size_t pitch0 = align_up((size_t)p->w, 64), istride0 = pitch0 * (size_t)p->h;
     const size_t c3 = (size_t)p->w * p->h * 3;
     size_t lane_bytes = 0;
-    size_t off_p0, off_n0, off_c3 = 0, off_flow[OFB_MAX_LEVELS], plan_base;
+    size_t off_p0, off_n0, off_c3 = 0, off_flow[OFB_MAX_LEVELS], off_total = 0, plan_base;
     PairPlan pl;
     {
         Carver cv;
@@ -846,6 +870,7 @@ int ofb_flow_pairs_host(ofb_ctx *c, const ofb_params *p, const unsigned char *pr
         off_n0 = cv.take(istride0 * sub);
         if (channels == 3) off_c3 = cv.take(c3 * sub * 2);
         for (int k = 0; k < p->levels; k++) off_flow[k] = cv.take((size_t)(p->w >> k) * (p->h >> k) * 8 * sub);
+        if (total_flow_h) off_total = cv.take((size_t)p->w * p->h * 8 * sub);
         plan_base = cv.off;
         Carver cv2;
         plan_pairs(&ps, &pl, &cv2);
@@ -853,6 +878,8 @@ int ofb_flow_pairs_host(ofb_ctx *c, const ofb_params *p, const unsigned char *pr
     }
     rc = ws_reserve(c, lane_bytes * OFB_LANES);
     if (rc) return rc;
+    for (int lane = 0; lane < OFB_LANES; lane++)
+        if ((rc = ws_acquire(c, c->lane_stream[lane]))) return rc;
     for (int first = 0, sb = 0; first < n; first += sub, sb++) {
         const int lane = sb % OFB_LANES;
         const int cnt = (n - first < sub) ? n - first : sub;
@@ -875,16 +902,47 @@ int ofb_flow_pairs_host(ofb_ctx *c, const ofb_params *p, const unsigned char *pr
         }
         float *flow_d[OFB_MAX_LEVELS];
         for (int k = 0; k < p->levels; k++) flow_d[k] = reinterpret_cast<float *>(B + off_flow[k]);
-        rc = run_pairs_device(c, &pc, pl, B + plan_base, B + off_p0, B + off_n0, pitch0, istride0, flow_d, nullptr, st);
+        float *total_d = total_flow_h ? reinterpret_cast<float *>(B + off_total) : nullptr;
+        // (one level: the total flow is the residual flow, the kernel has nothing to compose)
+        rc = run_pairs_device(c, &pc, pl, B + plan_base, B + off_p0, B + off_n0, pitch0, istride0, flow_d,
+                              p->levels > 1 ? total_d : nullptr, st);
         if (rc) return rc;
         for (int k = p->levels - 1; k >= 0; k--) {
+            if (!flow_levels_h || !flow_levels_h[k]) continue;
             const size_t per_pair = (size_t)(p->w >> k) * (p->h >> k) * 2; // floats
             OFB_CUDA_TRY(cudaMemcpyAsync(flow_levels_h[k] + per_pair * first, flow_d[k], per_pair * 4 * cnt,
+                                         cudaMemcpyDeviceToHost, st));
+        }
+        if (total_flow_h) {
+            const size_t per_pair = (size_t)p->w * p->h * 2;
+            OFB_CUDA_TRY(cudaMemcpyAsync(total_flow_h + per_pair * first, p->levels > 1 ? total_d : flow_d[0], per_pair * 4 * cnt,
                                          cudaMemcpyDeviceToHost, st));
         }
     }
     for (int lane = 0; lane < OFB_LANES; lane++) OFB_CUDA_TRY(cudaStreamSynchronize(c->lane_stream[lane]));
     return OFB_OK;
+}
+
+int ofb_flow_pairs_host(ofb_ctx *c, const ofb_params *p, const unsigned char *prev_h, const unsigned char *next_h,
+                        int channels, float *const *flow_levels_h)
+{
+    if (!flow_levels_h) {
+        set_error("flow_pairs_host: flow_levels_h is NULL");
+        return OFB_ERR_INVALID;
+    }
+    if (p)
+        for (int k = 0; k < p->levels && k < OFB_MAX_LEVELS; k++)
+            if (!flow_levels_h[k]) {
+                set_error("flow_levels_h[%d] is NULL", k);
+                return OFB_ERR_INVALID;
+            }
+    return flow_pairs_host_impl(c, p, prev_h, next_h, channels, flow_levels_h, nullptr);
+}
+
+int ofb_flow_pairs_host_ex(ofb_ctx *c, const ofb_params *p, const unsigned char *prev_h, const unsigned char *next_h,
+                           int channels, float *const *flow_levels_h, float *total_flow_h)
+{
+    return flow_pairs_host_impl(c, p, prev_h, next_h, channels, flow_levels_h, total_flow_h);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -904,6 +962,7 @@ int ofb_grayscale_avg_host_u8c3(ofb_ctx *c, const unsigned char *src_h, unsigned
     int rc = ws_reserve(c, cv.off);
     if (rc) return rc;
     cudaStream_t st = c->stream;
+    if ((rc = ws_acquire(c, st))) return rc;
     OFB_CUDA_TRY(cudaMemcpyAsync(c->ws + os, src_h, n, cudaMemcpyHostToDevice, st));
     rc = launch_grayscale(c->ws + os, w, h, c->ws + od, nullptr, 0, st, &c->launches);
     if (rc) return rc;
@@ -927,6 +986,7 @@ int ofb_bilinear_filter_host_u8c3(ofb_ctx *c, const unsigned char *src, const un
     int rc = ws_reserve(c, cv.off);
     if (rc) return rc;
     cudaStream_t st = c->stream;
+    if ((rc = ws_acquire(c, st))) return rc;
     OFB_CUDA_TRY(cudaMemcpyAsync(c->ws + os, src, n, cudaMemcpyHostToDevice, st));
     const uint8_t *gd = c->ws + os;
     if (gray != src) {
@@ -972,6 +1032,7 @@ int ofb_conv_3ch_1ch_u8_u8_host(ofb_ctx *c, const unsigned char *src_h, int w, i
     int rc = ws_reserve(c, cv.off);
     if (rc) return rc;
     cudaStream_t st = c->stream;
+    if ((rc = ws_acquire(c, st))) return rc;
     OFB_CUDA_TRY(cudaMemcpyAsync(c->ws + os, src_h, n * 3, cudaMemcpyHostToDevice, st));
     rc = launch_conv_c3_u8(c->ws + os, w, h, c->ws + od, mask, mw, mh, st, &c->launches);
     if (rc) return rc;
@@ -995,6 +1056,7 @@ int ofb_debug_view_host_u8c3(ofb_ctx *c, const unsigned char *prev_level_h, cons
     int rc = ws_reserve(c, cv.off);
     if (rc) return rc;
     cudaStream_t st = c->stream;
+    if ((rc = ws_acquire(c, st))) return rc;
     OFB_CUDA_TRY(cudaMemcpyAsync(c->ws + oc, cur_level_h, n * 3, cudaMemcpyHostToDevice, st));
     if (which == OFB_VIEW_T) OFB_CUDA_TRY(cudaMemcpyAsync(c->ws + op, prev_level_h, n * 3, cudaMemcpyHostToDevice, st));
     rc = launch_debug_view(c->ws + op, c->ws + oc, w, h, level, which, c->ws + oo, st, &c->launches);
@@ -1029,6 +1091,7 @@ int ofb_compose_flow_host(ofb_ctx *c, float *const *flow_pyramid_h, int w, int h
     int rc = ws_reserve(c, cv.off);
     if (rc) return rc;
     cudaStream_t st = c->stream;
+    if ((rc = ws_acquire(c, st))) return rc;
     for (int k = level; k < levels; k++)
         OFB_CUDA_TRY(cudaMemcpyAsync(c->ws + off_res[k], flow_pyramid_h[k], (size_t)(w >> k) * (h >> k) * 8,
                                      cudaMemcpyHostToDevice, st));
@@ -1183,7 +1246,14 @@ int ofb_stream_create(ofb_ctx *c, const ofb_params *p, int bil_win, double bil_s
         delete s;
         return OFB_ERR_NOMEM;
     }
-    OFB_CUDA_TRY(cudaMemsetAsync(s->mem, 0, cv.off, c->stream));
+    e = cudaMemsetAsync(s->mem, 0, cv.off, c->stream);
+    if (e != cudaSuccess) {
+        set_error("stream cudaMemsetAsync failed: %s", cudaGetErrorString(e));
+        cudaGetLastError();
+        cudaFree(s->mem);
+        delete s;
+        return OFB_ERR_CUDA;
+    }
     *out = s;
     return OFB_OK;
 }
@@ -1213,8 +1283,19 @@ int ofb_stream_push_bgr_host(ofb_stream *s, const unsigned char *frame_bgr, floa
         return OFB_ERR_INVALID;
     }
     ofb_ctx *c = s->ctx;
-    OFB_GUARD(c);
     const ofb_params &p = s->p;
+    if (s->frames > 0) { // (before anything is enqueued: a rejected call leaves the sequence where it was)
+        if (!flow_levels_h) {
+            set_error("stream_push: flow_levels_h is NULL");
+            return OFB_ERR_INVALID;
+        }
+        for (int k = 0; k < p.levels; k++)
+            if (!flow_levels_h[k]) {
+                set_error("stream_push: flow_levels_h[%d] is NULL", k);
+                return OFB_ERR_INVALID;
+            }
+    }
+    OFB_GUARD(c);
     cudaStream_t st = c->stream;
     uint8_t *B = s->mem;
     const int cur = s->cur, prv = cur ^ 1;
@@ -1236,10 +1317,6 @@ int ofb_stream_push_bgr_host(ofb_stream *s, const unsigned char *frame_bgr, floa
         if (rc) return rc;
     }
     if (s->frames > 0) {
-        if (!flow_levels_h) {
-            set_error("stream_push: flow_levels_h is NULL");
-            return OFB_ERR_INVALID;
-        }
         for (int k = p.levels - 1; k >= 0; k--) { // main.cu:256-262
             LkLevelArgs a{};
             a.prev = B + s->off_pyr[prv][k];
@@ -1255,7 +1332,7 @@ int ofb_stream_push_bgr_host(ofb_stream *s, const unsigned char *frame_bgr, floa
             a.flow_scale = p.flow_scale;
             a.flow_out = reinterpret_cast<float *>(B + s->off_flow[k]);
             a.sm_count = c->sm_count;
-    a.solve_fast = c->solve_fast;
+            a.solve_fast = c->solve_fast;
             if (k < p.levels - 1) {
                 a.cum_in = reinterpret_cast<const float *>(k + 1 == p.levels - 1 ? B + s->off_flow[k + 1] : B + s->off_cum[k + 1]);
                 a.cum_w = p.w >> (k + 1);
@@ -1265,10 +1342,6 @@ int ofb_stream_push_bgr_host(ofb_stream *s, const unsigned char *frame_bgr, floa
             else if (k <= p.levels - 2) a.cum_out = reinterpret_cast<float *>(B + s->off_cum[k]);
             rc = launch_lk_level(a, st, &c->launches);
             if (rc) return rc;
-            if (!flow_levels_h[k]) {
-                set_error("stream_push: flow_levels_h[%d] is NULL", k);
-                return OFB_ERR_INVALID;
-            }
             OFB_CUDA_TRY(cudaMemcpyAsync(flow_levels_h[k], B + s->off_flow[k], (size_t)(p.w >> k) * (p.h >> k) * 8,
                                          cudaMemcpyDeviceToHost, st));
         }

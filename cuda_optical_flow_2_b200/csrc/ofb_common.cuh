@@ -19,6 +19,30 @@ void set_error(const char *fmt, ...);
         }                                                                                               \
     } while (0)
 
+// Makes `dev` current for the lifetime of the guard and restores the caller's device afterwards (every entry point of the
+// C ABI uses it: a host that drives several GPUs from one thread keeps its own current device).
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = false;
+    explicit DeviceGuard(int dev)
+    {
+        if (cudaGetDevice(&prev) != cudaSuccess) {
+            prev = -1;
+            set_error("no usable CUDA device: %s", cudaGetErrorString(cudaGetLastError()));
+            return;
+        }
+        if (prev != dev && cudaSetDevice(dev) != cudaSuccess) {
+            set_error("cudaSetDevice(%d) failed: %s", dev, cudaGetErrorString(cudaGetLastError()));
+            return;
+        }
+        ok = true;
+    }
+    ~DeviceGuard()
+    {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
 // ---- fused LK level (lk_level.cu) ----------------------------------------------------------
 struct LkLevelArgs {
     const uint8_t *prev;   // planar u8, local rows [0, h_local)

@@ -24,6 +24,7 @@
 #include <algorithm>
 #include <cstring>
 #include <mutex>
+#include <new>
 #include <vector>
 
 struct ofb_ctx; // ofb_api.cu
@@ -255,6 +256,17 @@ __global__ void peer_wait_kernel(const __grid_constant__ PeerWaitArgs a)
     if (threadIdx.x < a.n && !peer_spin(a.flag[threadIdx.x], *a.pairs + 1u)) atomicOr(a.err, 2);
     __threadfence_system();
 }
+// Teardown: wait until every rank this one pushed to has acknowledged this rank's last pair (done[dst] == pairs).
+struct PeerDrainArgs {
+    const unsigned *flag[2 * PEER_MAX_DST];
+    int n;
+    const unsigned *pairs;
+    int *err;
+};
+__global__ void peer_drain_kernel(const __grid_constant__ PeerDrainArgs a)
+{
+    if (threadIdx.x < a.n && !peer_spin(a.flag[threadIdx.x], *a.pairs)) atomicOr(a.err, 2);
+}
 // End of a pair: tell every rank that pushes to me that its rows have been used, and count the pair.
 __global__ void peer_done_kernel(const __grid_constant__ PeerDoneArgs a)
 {
@@ -266,6 +278,10 @@ __global__ void peer_done_kernel(const __grid_constant__ PeerDoneArgs a)
 } // namespace ofb
 
 using namespace ofb;
+
+#define OFB_STRIPS_GUARD(st)                       \
+    DeviceGuard _guard(ctx_device((st)->ctx));     \
+    if (!_guard.ok) return OFB_ERR_CUDA
 
 struct ofb_strips {
     ofb_ctx *ctx = nullptr;
@@ -291,6 +307,7 @@ struct ofb_strips {
     std::vector<ArenaLayout> peer_lay;
     std::vector<void *> ipc_opened;
     bool peers_connected = false;
+    std::vector<int> done_from;             // ranks this one pushes to: they write done[rank] into this arena (teardown waits for it)
 };
 
 namespace {
@@ -321,12 +338,13 @@ inline unsigned *flag_ptr(uint8_t *arena, const ArenaLayout &lay, size_t index)
     return reinterpret_cast<unsigned *>(arena + lay.flags) + index;
 }
 // Exchange x of the pair with epoch `epoch`: push `sends`, then wait for the ranks in `sources`.
+// (do_push / do_wait: the two halves, which ofb_strips_run_phase_device enqueues separately.)
 int peer_exchange(ofb_strips *st, int x, const std::vector<PeerSend> &sends, const std::vector<int> &sources, cudaStream_t q,
-                  unsigned long long *launches)
+                  unsigned long long *launches, bool do_push = true, bool do_wait = true)
 {
     const int world = st->plan.world, L = st->plan.levels, me = st->rank;
     unsigned *pairs = flag_ptr(st->arena, st->lay, (size_t)(L + 1) * world + L);
-    if (!sends.empty()) {
+    if (do_push && !sends.empty()) {
         PeerPushArgs a{};
         size_t total = 0;
         for (const PeerSend &sd : sends) {
@@ -346,6 +364,7 @@ int peer_exchange(ofb_strips *st, int x, const std::vector<PeerSend> &sends, con
                 a.arrive[a.ndst] = flag_ptr(st->peer_arena[sd.peer], st->peer_lay[sd.peer], (size_t)x * world + me);
                 a.done_local[a.ndst] = flag_ptr(st->arena, st->lay, (size_t)L * world + sd.peer);
                 a.ndst++;
+                if (std::find(st->done_from.begin(), st->done_from.end(), sd.peer) == st->done_from.end()) st->done_from.push_back(sd.peer);
             }
         }
         a.counter = flag_ptr(st->arena, st->lay, (size_t)(L + 1) * world + x);
@@ -356,7 +375,7 @@ int peer_exchange(ofb_strips *st, int x, const std::vector<PeerSend> &sends, con
         OFB_CUDA_TRY(cudaGetLastError());
         if (launches) ++*launches;
     }
-    if (!sources.empty()) {
+    if (do_wait && !sources.empty()) {
         PeerWaitArgs w{};
         for (int src : sources) {
             if (w.n == PEER_MAX_DST) {
@@ -443,8 +462,14 @@ int ofb_strips_create(ofb_ctx *ctx, int w, int h, int levels, int win, int warp_
         set_error("coarsest level has %d rows, cannot cut it into %d strips", hc, world);
         return OFB_ERR_INVALID;
     }
-    OFB_CUDA_TRY(cudaSetDevice(ctx_device(ctx)));
-    ofb_strips *st = new ofb_strips;
+    DeviceGuard guard(ctx_device(ctx));
+    if (!guard.ok) return OFB_ERR_CUDA;
+    ofb_strips *st = new (std::nothrow) ofb_strips;
+    if (!st) {
+        set_error("strips_create: out of host memory");
+        return OFB_ERR_NOMEM;
+    }
+    try { // (std::vector growth below must not throw across the C ABI)
     st->ctx = ctx;
     st->rank = rank;
     st->warp_mode = warp_mode;
@@ -547,6 +572,12 @@ int ofb_strips_create(ofb_ctx *ctx, int w, int h, int levels, int win, int warp_
         delete st;
         return rc;
     }
+    } catch (const std::bad_alloc &) {
+        for (void *p : st->allocs) cudaFree(p);
+        delete st;
+        set_error("strips_create: out of host memory");
+        return OFB_ERR_NOMEM;
+    }
     *out = st;
     return OFB_OK;
 }
@@ -560,7 +591,7 @@ int ofb_strips_peer_handle(ofb_strips *st, void *blob128)
         set_error("strips_peer_handle: bad arguments");
         return OFB_ERR_INVALID;
     }
-    OFB_CUDA_TRY(cudaSetDevice(ctx_device(st->ctx)));
+    OFB_STRIPS_GUARD(st);
     memset(blob128, 0, 128);
     cudaIpcMemHandle_t h;
     OFB_CUDA_TRY(cudaIpcGetMemHandle(&h, st->arena));
@@ -626,7 +657,7 @@ int ofb_strips_peer_connect(ofb_strips *st, const void *blobs)
         set_error("strips_peer_connect: bad arguments");
         return OFB_ERR_INVALID;
     }
-    OFB_CUDA_TRY(cudaSetDevice(ctx_device(st->ctx)));
+    OFB_STRIPS_GUARD(st);
     const int world = st->plan.world;
     st->peer_arena.assign(world, nullptr);
     st->peer_arena[st->rank] = st->arena;
@@ -658,14 +689,32 @@ int ofb_strips_peer_connect_local(ofb_strips *st, void *const *arenas)
     return finish_connect(st);
 }
 
+// Teardown.  The last thing a neighbour writes into this rank's arena is its `done` flag at the end of its last pair,
+// which can land after this rank has finished its own: so, before the arena is unmapped and freed, wait (on the device,
+// bounded like every other wait) until every rank this one pushes to has acknowledged this rank's last pair.  Ranks must
+// have run the same number of pairs; a rank that is still PUSHING a further pair into a freed arena is a caller error.
 int ofb_strips_destroy(ofb_strips *st)
 {
     if (!st) return OFB_OK;
-    cudaSetDevice(ctx_device(st->ctx));
-    cudaDeviceSynchronize();
-    for (void *p : st->ipc_opened) cudaIpcCloseMemHandle(p);
-    if (st->comm && nccl()) nccl()->CommDestroy(st->comm);
-    for (void *p : st->allocs) cudaFree(p);
+    {
+        DeviceGuard guard(ctx_device(st->ctx));
+        if (guard.ok) {
+            cudaDeviceSynchronize();
+            if (st->plan.world > 1 && st->peers_connected && !st->comm && !st->done_from.empty()) {
+                PeerDrainArgs d{};
+                const int L = st->plan.levels, world = st->plan.world;
+                for (int dst : st->done_from)
+                    if (d.n < 2 * PEER_MAX_DST) d.flag[d.n++] = flag_ptr(st->arena, st->lay, (size_t)L * world + dst);
+                d.pairs = flag_ptr(st->arena, st->lay, (size_t)(L + 1) * world + L);
+                d.err = st->overflow;
+                peer_drain_kernel<<<1, 32>>>(d);
+                cudaDeviceSynchronize();
+            }
+            for (void *p : st->ipc_opened) cudaIpcCloseMemHandle(p);
+            if (st->comm && nccl()) nccl()->CommDestroy(st->comm);
+            for (void *p : st->allocs) cudaFree(p);
+        }
+    }
     delete st;
     return OFB_OK;
 }
@@ -724,13 +773,22 @@ int ofb_strips_set_total(ofb_strips *st, int on)
 
 // One pair: own rows of level 0 in, residual (and cumulative) flow of the own rows of every level out, all
 // asynchronous on `stream`.  prev_own_d / next_own_d: rows [y0, y1) of level 0, planar u8 with `pitch` bytes per row.
-int ofb_strips_run_device(ofb_strips *st, const uint8_t *prev_own_d, const uint8_t *next_own_d, size_t pitch, void *stream)
+//
+// `phase` < 0: the whole pair.  Otherwise one of its 2L phases (peer-memory transport only), so that a host can interleave
+// the ranks of ONE process on ONE stream in an order in which no kernel ever waits for a later one:
+//   phase 0      own-row upload, push of the level-0 image rows (exchange 0)
+//   phase 1      wait for exchange 0, pyramid, coarsest level L-1
+//   phase 2j     push of the cumulative-flow rows of level L-j (exchange j),            j = 1 .. L-1
+//   phase 2j+1   wait for exchange j, level L-1-j; after level 0 the end-of-pair handshake
+static int strips_run_impl(ofb_strips *st, const uint8_t *prev_own_d, const uint8_t *next_own_d, size_t pitch, void *stream, int phase)
 {
     if (!st || !prev_own_d || !next_own_d) {
         set_error("strips_run: bad arguments");
         return OFB_ERR_INVALID;
     }
-    OFB_CUDA_TRY(cudaSetDevice(ctx_device(st->ctx)));
+    OFB_STRIPS_GUARD(st);
+    try { // (std::vector growth must not throw across the C ABI)
+    auto on = [phase](int ph) { return phase < 0 || phase == ph; };
     cudaStream_t q = static_cast<cudaStream_t>(stream);
     const StripPlan &pl = st->plan;
     const bool peer_mode = pl.world > 1 && !st->comm;
@@ -739,6 +797,10 @@ int ofb_strips_run_device(ofb_strips *st, const uint8_t *prev_own_d, const uint8
         return OFB_ERR_INVALID;
     }
     NcclApi *n = pl.world > 1 && !peer_mode ? nccl() : nullptr;
+    if (phase >= 0 && (n || phase >= 2 * pl.levels)) {
+        set_error("strips_run_phase: phase %d of %d (phases exist for the peer-memory transport and one rank only)", phase, 2 * pl.levels);
+        return OFB_ERR_INVALID;
+    }
     unsigned long long *launches = ctx_launch_counter(st->ctx);
     const int L = pl.levels, me = st->rank;
     std::vector<int> all_sources; // every rank that pushes to me during the pair
@@ -746,7 +808,7 @@ int ofb_strips_run_device(ofb_strips *st, const uint8_t *prev_own_d, const uint8
         set_error("strips_run: pitch %zu smaller than the width %d", pitch, pl.W);
         return OFB_ERR_INVALID;
     }
-    {
+    if (on(0)) {
         const LevelStrip &s = st->s[0];
         const size_t off = (size_t)(s.y0 - s.eb0) * st->pitch[0];
         // a producer that wrote the own rows in place (ofb_strips_input) saves this copy
@@ -757,7 +819,7 @@ int ofb_strips_run_device(ofb_strips *st, const uint8_t *prev_own_d, const uint8
             OFB_CUDA_TRY(cudaMemcpy2DAsync(st->next[0] + off, st->pitch[0], next_own_d, pitch, (size_t)s.w, (size_t)(s.y1 - s.y0),
                                            cudaMemcpyDeviceToDevice, q));
     }
-    OFB_CUDA_TRY(cudaMemsetAsync(st->overflow, 0, sizeof(int), q));
+    // (the error flag st->overflow is sticky: kernels OR into it, only ofb_strips_check clears it)
     // ONE image exchange, on level 0: the rows of my buffer that other ranks own (and vice versa), in place
     if (n) {
         const LevelStrip &s = st->s[0];
@@ -797,11 +859,11 @@ int ofb_strips_run_device(ofb_strips *st, const uint8_t *prev_own_d, const uint8
                 add_unique(all_sources, peer);
             }
         }
-        int rc = peer_exchange(st, 0, sends, sources, q, launches);
+        int rc = peer_exchange(st, 0, sends, sources, q, launches, on(0), on(1));
         if (rc) return rc;
     }
     // pyramid: every buffer row of level k+1 from the buffer rows of level k (halo rows are built locally)
-    for (int k = 0; k + 1 < L; k++) {
+    for (int k = 0; on(1) && k + 1 < L; k++) {
         const LevelStrip &s = st->s[k], &d = st->s[k + 1];
         int rc = launch_pyr_down_strip(st->prev[k], st->pitch[k], s.w, s.eb1 - s.eb0, s.eb0, st->prev[k + 1], st->pitch[k + 1], d.eb0,
                                        d.eb1, q, launches, 2, st->img_stride[k], st->img_stride[k + 1]);
@@ -843,10 +905,12 @@ int ofb_strips_run_device(ofb_strips *st, const uint8_t *prev_own_d, const uint8
                         add_unique(all_sources, peer);
                     }
                 }
-                int rc = peer_exchange(st, L - 1 - k, sends, sources, q, launches); // exchanges 1 .. L-1
+                const int x = L - 1 - k; // exchanges 1 .. L-1
+                int rc = peer_exchange(st, x, sends, sources, q, launches, on(2 * x), on(2 * x + 1));
                 if (rc) return rc;
             }
         }
+        if (!on(2 * (L - 1 - k) + 1)) continue;
         LkLevelArgs a{};
         a.prev = st->prev[k];
         a.next = st->next[k];
@@ -878,7 +942,7 @@ int ofb_strips_run_device(ofb_strips *st, const uint8_t *prev_own_d, const uint8
         int rc = launch_lk_level(a, q, launches);
         if (rc) return rc;
     }
-    if (peer_mode) { // the rows my neighbours pushed have been used: they may push the next pair's
+    if (peer_mode && on(2 * L - 1)) { // the rows my neighbours pushed have been used: they may push the next pair's
         PeerDoneArgs d{};
         for (int src : all_sources) {
             if (d.n == 2 * PEER_MAX_DST) {
@@ -892,7 +956,26 @@ int ofb_strips_run_device(ofb_strips *st, const uint8_t *prev_own_d, const uint8
         OFB_CUDA_TRY(cudaGetLastError());
         if (launches) ++*launches;
     }
+    } catch (const std::bad_alloc &) {
+        set_error("strips_run: out of host memory");
+        return OFB_ERR_NOMEM;
+    }
     return OFB_OK;
+}
+
+int ofb_strips_run_device(ofb_strips *st, const uint8_t *prev_own_d, const uint8_t *next_own_d, size_t pitch, void *stream)
+{
+    return strips_run_impl(st, prev_own_d, next_own_d, pitch, stream, -1);
+}
+
+int ofb_strips_run_phase_device(ofb_strips *st, const uint8_t *prev_own_d, const uint8_t *next_own_d, size_t pitch, int phase,
+                                void *stream)
+{
+    if (phase < 0) {
+        set_error("strips_run_phase: phase %d", phase);
+        return OFB_ERR_INVALID;
+    }
+    return strips_run_impl(st, prev_own_d, next_own_d, pitch, stream, phase);
 }
 
 // Synchronises the stream and reports whether a warp sample reached past the exchanged halo rows (the result is
@@ -903,9 +986,11 @@ int ofb_strips_check(ofb_strips *st, void *stream, int *overflow)
         set_error("strips_check: NULL handle");
         return OFB_ERR_INVALID;
     }
-    OFB_CUDA_TRY(cudaSetDevice(ctx_device(st->ctx)));
+    OFB_STRIPS_GUARD(st);
     int v = 0;
+    // sticky flag: everything since the last check; read, then clear (in stream order, so pairs enqueued later start clean)
     OFB_CUDA_TRY(cudaMemcpyAsync(&v, st->overflow, sizeof(int), cudaMemcpyDeviceToHost, static_cast<cudaStream_t>(stream)));
+    OFB_CUDA_TRY(cudaMemsetAsync(st->overflow, 0, sizeof(int), static_cast<cudaStream_t>(stream)));
     OFB_CUDA_TRY(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
     if (overflow) *overflow = v;
     return OFB_OK;

@@ -393,6 +393,7 @@ class NativeStrips:
             raise ValueError(f"unknown strip transport {transport!r}")
         self.torch, self.C, self.L, self.lib, self.ctx = torch, C, L, L.load(), ctx
         self.w, self.h, self.levels, self.dev, self.world, self.rank = w, h, levels, device, world, rank
+        self._transport = transport
         idbuf = torch.zeros(128, dtype=torch.uint8)
         use_nccl = world > 1 and transport == "nccl"
         if use_nccl:
@@ -464,7 +465,23 @@ class NativeStrips:
         self.L.check(self.lib.ofb_strips_run_device(self._h, prev_own.data_ptr(), next_own.data_ptr(), prev_own.stride(0),
                                                     self.C.c_void_p(stream)))
 
+    def run_phase(self, prev_own, next_own, phase: int, stream: int = 0) -> None:
+        """One of the 2 * levels phases of a pair (peer-memory transport); see run_local_sequenced."""
+        self.L.check(self.lib.ofb_strips_run_phase_device(self._h, prev_own.data_ptr(), next_own.data_ptr(), prev_own.stride(0),
+                                                          int(phase), self.C.c_void_p(stream)))
+
+    @staticmethod
+    def run_local_sequenced(ranks, inputs, stream: int = 0) -> None:
+        """One pair on ranks that live in ONE process and share ONE device (connect_local): phase p of every rank is
+        enqueued on `stream` before phase p + 1 of any, so every flag a kernel waits for has been raised by a kernel
+        AHEAD of it in the stream.  (Ranks that spin on each other from separate streams of one GPU are not
+        guaranteed to be co-scheduled; across GPUs each rank simply calls run().)"""
+        for phase in range(2 * ranks[0].levels):
+            for ns, (pin, nin) in zip(ranks, inputs):
+                ns.run_phase(pin, nin, phase, stream)
+
     def check(self, stream: int = 0) -> None:
+        """Synchronises; raises if any pair since the last check went wrong (the flag is sticky), and clears the flag."""
         v = self.C.c_int()
         self.L.check(self.lib.ofb_strips_check(self._h, self.C.c_void_p(stream), self.C.byref(v)))
         if v.value & 2:
@@ -482,13 +499,24 @@ class NativeStrips:
         return _device_view(self.torch, ptr, (y1 - y0, self.w >> level, 2), self.dev)
 
     def close(self) -> None:
+        """Collective across the ranks of a multi-process run: nobody frees the memory its neighbours write into before
+        everybody has finished (the library additionally waits for the neighbours' last acknowledgements)."""
         if getattr(self, "_h", None):
+            if self.world > 1 and self._transport != "local":
+                import torch.distributed as dist
+
+                if dist.is_available() and dist.is_initialized():
+                    self.torch.cuda.synchronize(self.dev)
+                    dist.barrier()
             self.lib.ofb_strips_destroy(self._h)
             self._h = None
 
     def __del__(self):
+        # (no collective from a finaliser: only the library-side bounded wait)
         try:
-            self.close()
+            if getattr(self, "_h", None):
+                self.lib.ofb_strips_destroy(self._h)
+                self._h = None
         except Exception:
             pass
 

@@ -71,6 +71,12 @@ int ofb_ctx_create(int device, ofb_ctx **out);
 int ofb_ctx_destroy(ofb_ctx *ctx);
 int ofb_ctx_device(const ofb_ctx *ctx, int *device);
 int ofb_ctx_sm_count(const ofb_ctx *ctx, int *sm_count);
+/* Threads and streams.  A context belongs to one host thread at a time.  All entry points share the context's one
+ * device workspace: a call on a stream waits (on the device, cudaStreamWaitEvent) for the previous call's use of it on
+ * another stream, so results are correct whatever streams are mixed, but two streams of one context never overlap --
+ * use one context per stream for that.  The workspace grows on demand; growing synchronises the device and frees the
+ * old block, which invalidates CUDA graphs captured from earlier calls: size it first with ofb_ctx_reserve_pairs. */
+int ofb_ctx_reserve_pairs(ofb_ctx *ctx, const ofb_params *p); /* workspace for ofb_flow_pairs_device with these parameters */
 /* Solve mode (OFB_SOLVE_*) of every fused-LK launch made through this context from now on. */
 int ofb_ctx_set_solve(ofb_ctx *ctx, int solve_mode);
 int ofb_ctx_get_solve(const ofb_ctx *ctx, int *solve_mode);
@@ -172,6 +178,12 @@ int ofb_inverse_matrix_f32_host(ofb_ctx *ctx, const float *sumIx2, const float *
  * asynchronous; pageable memory works too. */
 int ofb_flow_pairs_host(ofb_ctx *ctx, const ofb_params *p, const unsigned char *prev_h, const unsigned char *next_h,
                         int channels, float *const *flow_levels_h);
+/* The same loop with the outputs chosen by the caller: flow_levels_h may be NULL or hold NULL entries (levels that stay
+ * on the device), total_flow_h (may be NULL) receives the level-0 composition of main.cu:136-147, n_pairs * h * w * 2
+ * floats -- what visualizeFlowField consumes.  Planar gray in (channels = 1) and the total flow only out moves 10 bytes
+ * per pixel over PCIe instead of the 16.5 of the reference layout with every level. */
+int ofb_flow_pairs_host_ex(ofb_ctx *ctx, const ofb_params *p, const unsigned char *prev_h, const unsigned char *next_h,
+                           int channels, float *const *flow_levels_h, float *total_flow_h);
 
 /* ------------------------------------------------------------------------------------------
  * Pre-processing and the frame loop of main.cu
@@ -224,7 +236,16 @@ int ofb_stream_destroy(ofb_stream *s);
  *   ofb_strips_nccl_unique_id : rank 0 makes the 128-byte id, the application broadcasts it (any transport)
  *   ofb_strips_create         : collective over all ranks when a NCCL id is given (ncclCommInitRank)
  *   ofb_strips_check          : synchronises; *overflow bit 0 = a warp sample reached past the halo rows, bit 1 = a
- *                               neighbour's rows did not arrive within 4 s (peer-memory transport)
+ *                               neighbour's rows did not arrive within 4 s (peer-memory transport).  The flag is sticky:
+ *                               it covers every pair since the previous check, which clears it
+ *   ofb_strips_run_phase_device: one of the 2 * levels phases of a pair (peer-memory transport): 0 = upload + push of the
+ *                               level-0 image rows; 1 = wait, pyramid, coarsest level; 2j = push of the cumulative flow of
+ *                               level L-j; 2j+1 = wait, level L-1-j (j = 1 .. L-1).  A host that runs several ranks in ONE
+ *                               process on ONE stream (tests on a single GPU) enqueues phase p of every rank before phase
+ *                               p+1 of any: no kernel then ever waits for a kernel enqueued after it
+ *   ofb_strips_destroy        : waits (bounded) until every neighbour has acknowledged this rank's last pair before its
+ *                               arena is unmapped and freed; all ranks must have run the same number of pairs.  Across
+ *                               processes also put a barrier between the last check and the destroy calls
  *   ofb_strips_run_device     : prev_own_d / next_own_d = rows [y0, y1) of level 0 (ofb_strips_own_rows), planar u8
  *   ofb_strips_result         : device pointers to the own rows of the residual flow / cumulative flow of a level
  *   ofb_strips_input          : where the own rows of level 0 live inside the handle: a producer that writes them there
@@ -237,6 +258,8 @@ int ofb_strips_create(ofb_ctx *ctx, int w, int h, int levels, int win, int warp_
                       int reach, const void *nccl_id128, ofb_strips **out);
 int ofb_strips_own_rows(const ofb_strips *s, int level, int *y0, int *y1);
 int ofb_strips_run_device(ofb_strips *s, const uint8_t *prev_own_d, const uint8_t *next_own_d, size_t pitch, void *stream);
+int ofb_strips_run_phase_device(ofb_strips *s, const uint8_t *prev_own_d, const uint8_t *next_own_d, size_t pitch, int phase,
+                                void *stream);
 int ofb_strips_result(const ofb_strips *s, int level, float **flow_own_d, float **total_own_d);
 int ofb_strips_check(ofb_strips *s, void *stream, int *overflow);
 int ofb_strips_destroy(ofb_strips *s);

@@ -3,10 +3,6 @@ import sys
 
 import pytest
 
-# The peer-memory strip test runs up to eight ranks as eight streams of ONE process; each needs its own hardware queue
-# (a rank's wait kernel spins until another rank's copy kernel has run), so raise the default of 8 before CUDA starts.
-os.environ["CUDA_DEVICE_MAX_CONNECTIONS"] = "32"
-
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)

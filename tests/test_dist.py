@@ -221,11 +221,13 @@ def test_native_strip_runner_world_one_equals_whole_frame(ctx, oracle, W, H, lev
 @pytest.mark.parametrize("W,H,levels,win,world", [(640, 480, 3, 9, 2), (322, 406, 2, 5, 3), (1920, 1080, 4, 15, 4),
                                                    (7680, 4320, 4, 9, 8)])
 def test_native_strips_peer_memory_transport_equals_whole_frame(ctx, oracle, W, H, levels, win, world):
-    """csrc/strips.cu with the peer-memory transport: `world` ranks live in this process on one GPU, each with its own
-    stream; the sender's copy kernel stores halo rows straight into the receiver's arena and raises an epoch flag, the
-    receiver's wait kernel spins on it.  Three pairs back to back (flags, epochs and the done handshake are re-used),
-    each bit for bit the whole-frame result.  Across processes the same kernels run on CUDA IPC mappings
-    (scripts/run_strips.py --native --transport peer under torchrun)."""
+    """csrc/strips.cu with the peer-memory transport: `world` ranks live in this process on one GPU; the sender's copy
+    kernel stores halo rows straight into the receiver's arena and raises an epoch flag, the receiver's wait kernel
+    checks it.  All ranks share ONE stream and their pairs are enqueued phase by phase (run_local_sequenced), so every
+    flag is raised by a kernel ahead of its waiter: kernels of different ranks never have to be co-scheduled on the one
+    GPU.  Three pairs back to back (flags, epochs and the done handshake are re-used), each bit for bit the whole-frame
+    result.  Across processes the same kernels run on CUDA IPC mappings, each rank enqueuing its whole pair at once
+    (test_native_strips_two_processes_over_cuda_ipc, bench.py under torchrun)."""
     import torch
 
     from cuda_optical_flow_2_b200 import WARP_BILINEAR, planar_to_device
@@ -253,11 +255,10 @@ def test_native_strips_peer_memory_transport_equals_whole_frame(ctx, oracle, W, 
                     inputs.append((pin, nin))
                 else:
                     inputs.append((dp[0, y0:y1], dn[0, y0:y1]))
-            torch.cuda.synchronize()  # (no host synchronisation between the ranks' run() calls: a rank waits for its neighbours)
-            for ns, st, (pin, nin) in zip(ranks, streams, inputs):
-                ns.run(pin, nin, st.cuda_stream)
-            for ns, st in zip(ranks, streams):
-                ns.check(st.cuda_stream)
+            torch.cuda.synchronize()
+            NativeStrips.run_local_sequenced(ranks, inputs, streams[0].cuda_stream)
+            for ns in ranks:
+                ns.check(streams[0].cuda_stream)
             for ns in ranks:
                 for k in range(levels):
                     y0, y1 = ns.own_rows(k)
@@ -278,8 +279,9 @@ def test_native_strips_peer_memory_transport_equals_whole_frame(ctx, oracle, W, 
 
 @pytest.mark.gpu
 def test_native_strips_peer_memory_pair_replays_as_cuda_graph(ctx, oracle):
-    """The peer-memory transport has no host-side state per pair (the epoch lives in device memory), so one pair of a
-    rank is capturable as a CUDA graph; the replays stay bit for bit the whole-frame result."""
+    """The peer-memory transport has no host-side state per pair (the epoch lives in device memory), so a pair is
+    capturable as a CUDA graph; the replays stay bit for bit the whole-frame result.  (Both ranks of this one-GPU test
+    are captured into one graph, phase by phase; across GPUs each rank captures its own run().)"""
     import torch
 
     from cuda_optical_flow_2_b200 import WARP_BILINEAR, planar_to_device
@@ -306,20 +308,15 @@ def test_native_strips_peer_memory_pair_replays_as_cuda_graph(ctx, oracle):
             return whole
 
         load(11, 1.0, 1.0)
-        for ns, st, (pin, nin) in zip(ranks, streams, ins):  # warm-up pair, eager
-            ns.run(pin, nin, st.cuda_stream)
+        NativeStrips.run_local_sequenced(ranks, ins, streams[0].cuda_stream)  # warm-up pair, eager
         torch.cuda.synchronize()
-        graphs = []
-        for ns, st, (pin, nin) in zip(ranks, streams, ins):
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g, stream=st, capture_error_mode="thread_local"):
-                ns.run(pin, nin, torch.cuda.current_stream(dev).cuda_stream)
-            graphs.append(g)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=streams[0], capture_error_mode="thread_local"):
+            NativeStrips.run_local_sequenced(ranks, ins, torch.cuda.current_stream(dev).cuda_stream)
         for trial, (dx, dy) in enumerate([(2.25, -1.5), (-3.0, 0.75)]):
             whole = load(20 + trial, dx, dy)
-            for g, st in zip(graphs, streams):  # each rank on its own stream: a rank waits for its neighbour
-                with torch.cuda.stream(st):
-                    g.replay()
+            with torch.cuda.stream(streams[0]):
+                g.replay()
             torch.cuda.synchronize()
             for ns in ranks:
                 ns.check(0)
@@ -333,6 +330,36 @@ def test_native_strips_peer_memory_pair_replays_as_cuda_graph(ctx, oracle):
         torch.cuda.synchronize()
         for ns in ranks:
             ns.close()
+
+
+@pytest.mark.gpu
+def test_native_strips_two_processes_over_cuda_ipc():
+    """Two PROCESSES, one GPU each, connected over CUDA IPC (the peer-memory transport as bench.py runs it under
+    torchrun): rows pushed into the neighbour's arena over NVLink, two pairs in flight, bit for bit the whole-frame
+    result.  Skipped on a one-GPU box."""
+    import json
+    import socket
+    import subprocess
+    import sys
+
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    with socket.socket() as sk:
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", str(port), os.path.join(root, "bench.py"), "--strips-only", "--strips-size", "1920x1080x3",
+           "--strips-reps", "6"]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads([ln for ln in out.stdout.splitlines() if ln.startswith("{")][-1])
+    rec = line["strips"]
+    assert rec["n_ranks"] == 2 and rec["transport"] == "peer"
+    assert rec["bit_identical_to_whole_frame"] is True
+    assert rec["in_flight_2"]["bit_identical_to_whole_frame"] is True
 
 
 def test_native_strip_plan_matches_python_plan():

@@ -62,6 +62,17 @@ def test_flow_arrows_equal_reference_rule(ctx, oracle, level, arrow_res):
 
 
 @pytest.mark.gpu
+def test_flow_arrows_dense_grid(ctx, oracle):
+    """arrow_res above half the width: the grid step is 1 and every pixel is a grid point (more arrows than
+    arrow_res + 2 per row, which an earlier capacity guess assumed)."""
+    w, h, levels = 100, 100, 1
+    fl = _pyramid(w, h, levels, seed=5)
+    got = ctx.flow_arrows(fl, w, h, levels, 0, 60)
+    ref = oracle.flow_arrows(fl, 0, 60)
+    assert got.shape == ref.shape and np.array_equal(got, ref) and got.shape[0] > 62 * 62
+
+
+@pytest.mark.gpu
 def test_compose_flow_equals_fused_total_flow(ctx, oracle):
     """The device path's total flow (cumulative output of the level-0 kernel) is the same composition."""
     import torch
