@@ -84,13 +84,22 @@ static int ws_reserve(ofb_ctx *c, size_t bytes)
 }
 
 // Orders the uses of the shared workspace across streams (see ofb_ctx::ws_event).
+// A stream that is being captured into a CUDA graph takes no part: a capture cannot depend on eager work of another
+// stream, and an event recorded inside a capture belongs to the graph.  Replays of such a graph are ordered against the
+// context's other users by their caller (one context per concurrently used stream is the simple rule).
+static bool ws_capturing(cudaStream_t st)
+{
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    return cudaStreamIsCapturing(st, &cap) == cudaSuccess && cap != cudaStreamCaptureStatusNone;
+}
 static int ws_acquire(ofb_ctx *c, cudaStream_t st)
 {
-    if (c->ws_busy && c->ws_stream != st) OFB_CUDA_TRY(cudaStreamWaitEvent(st, c->ws_event, 0));
+    if (c->ws_busy && c->ws_stream != st && !ws_capturing(st)) OFB_CUDA_TRY(cudaStreamWaitEvent(st, c->ws_event, 0));
     return OFB_OK;
 }
 static int ws_release(ofb_ctx *c, cudaStream_t st)
 {
+    if (ws_capturing(st)) return OFB_OK;
     OFB_CUDA_TRY(cudaEventRecord(c->ws_event, st));
     c->ws_stream = st;
     c->ws_busy = true;

@@ -75,7 +75,8 @@ int ofb_ctx_sm_count(const ofb_ctx *ctx, int *sm_count);
  * device workspace: a call on a stream waits (on the device, cudaStreamWaitEvent) for the previous call's use of it on
  * another stream, so results are correct whatever streams are mixed, but two streams of one context never overlap --
  * use one context per stream for that.  The workspace grows on demand; growing synchronises the device and frees the
- * old block, which invalidates CUDA graphs captured from earlier calls: size it first with ofb_ctx_reserve_pairs. */
+ * old block, which invalidates CUDA graphs captured from earlier calls: size it first with ofb_ctx_reserve_pairs.  A call made
+ * while its stream is being captured takes no part in that ordering (replays are ordered by their caller). */
 int ofb_ctx_reserve_pairs(ofb_ctx *ctx, const ofb_params *p); /* workspace for ofb_flow_pairs_device with these parameters */
 /* Solve mode (OFB_SOLVE_*) of every fused-LK launch made through this context from now on. */
 int ofb_ctx_set_solve(ofb_ctx *ctx, int solve_mode);
