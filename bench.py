@@ -663,7 +663,8 @@ def strips_block(env, ctx, w, h, levels, win, reps):
     torch.cuda.synchronize()
     plan = StripPlan(w, h, levels, win, world, 16)
     plan.validate()
-    handles = [NativeStrips(ctx, w, h, levels, win, world, rank, dev, WARP_BILINEAR, 1.0, 16, transport="peer") for _ in range(2)]
+    K = 4  # handles = pairs that can be in flight at once
+    handles = [NativeStrips(ctx, w, h, levels, win, world, rank, dev, WARP_BILINEAR, 1.0, 16, transport="peer") for _ in range(K)]
     ins = []
     for nat in handles:
         nat.set_total(False)
@@ -672,7 +673,7 @@ def strips_block(env, ctx, w, h, levels, win, reps):
         pin[:, :w].copy_(prev[0, y0:y1, :w])
         nin[:, :w].copy_(nxt[0, y0:y1, :w])
         ins.append((pin, nin))
-    streams = [torch.cuda.Stream(dev), torch.cuda.Stream(dev)]
+    streams = [torch.cuda.Stream(dev) for _ in range(K)]
 
     def identical(nat):
         ok = True
@@ -734,13 +735,19 @@ def strips_block(env, ctx, w, h, levels, win, reps):
         print(f"strips: graph capture failed ({ex!r}); eager", file=sys.stderr)
         ms, ok = measure(1, False)
         rec.update({"ms_per_pair": ms, "cuda_graph": False, "bit_identical_to_whole_frame": ok})
-    try:
-        ms2, ok2 = measure(2, rec["cuda_graph"])
-        rec["in_flight_2"] = {"ms_per_pair": ms2, "bit_identical_to_whole_frame": ok2,
-                              "what": "two handles on two streams, pairs alternate: a pair's late levels overlap the next pair's early ones"}
-    except Exception as ex:
-        rec["in_flight_2"] = {"error": repr(ex)}
-    best = min(rec["ms_per_pair"], rec.get("in_flight_2", {}).get("ms_per_pair") or 1e9)
+    rec["ms_per_pair_note"] = "one pair at a time on one stream: the latency of the whole dependency chain of a pair"
+    best = rec["ms_per_pair"]
+    for nf in (2, 4):
+        try:
+            ms2, ok2 = measure(nf, rec["cuda_graph"])
+            rec[f"in_flight_{nf}"] = {"ms_per_pair": ms2, "bit_identical_to_whole_frame": ok2}
+            if ok2:
+                best = min(best, ms2)
+        except Exception as ex:
+            rec[f"in_flight_{nf}"] = {"error": repr(ex)}
+    rec["in_flight_note"] = ("K handles on K streams, pairs alternate (throughput of a frame sequence): the late, small levels of a "
+                             "pair and its halo exchanges overlap the next pairs' early levels")
+    rec["ms_per_pair_pipelined"] = best
     rec["mpx_pairs_per_s"] = w * h / 1e6 / (best / 1e3)
     rec["halo_bytes_sent_rank0_per_pair"] = int(halo)
     peak, _ = measured_peak()
