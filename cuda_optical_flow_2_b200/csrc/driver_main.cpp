@@ -70,6 +70,7 @@ int main(int argc, char **argv)
     float step = 1.0f;
     const char *flo = nullptr; // --flo PREFIX: write PREFIX_<frame>.flo
     int arrow_res = 0;         // --arrows RES: count the arrows of visualizeFlowField(..., arrowRes)
+    int solve = OFB_SOLVE_EXACT; // --solve 0|1: bit-exact or tolerance-mode 2x2 solve
     for (int i = 1; i < argc; i++) {
         auto arg = [&](const char *n) { return !strcmp(argv[i], n) && i + 1 < argc; };
         if (arg("--w")) w = atoi(argv[++i]);
@@ -82,14 +83,16 @@ int main(int argc, char **argv)
         else if (arg("--batch")) batch = atoi(argv[++i]);
         else if (arg("--flo")) flo = argv[++i];
         else if (arg("--arrows")) arrow_res = atoi(argv[++i]);
+        else if (arg("--solve")) solve = atoi(argv[++i]);
         else {
-            fprintf(stderr, "usage: %s [--w W --h H --levels L --frames N --win WIN --warp 0|1|2 --step PX --batch N --flo PREFIX --arrows RES]\n", argv[0]);
+            fprintf(stderr, "usage: %s [--w W --h H --levels L --frames N --win WIN --warp 0|1|2 --solve 0|1 --step PX --batch N --flo PREFIX --arrows RES]\n", argv[0]);
             return 2;
         }
     }
     printf("Optical Flow (B200 path)\n=================\n%dx%d, %d levels, window %d, warp mode %d\n", w, h, levels, win, warp);
     gpu::set_lk_options(win, warp, 1.0f);
     if (!gpu::default_context()) return 1;
+    gpu::set_lk_solve(solve);
 
     if (batch > 0) { // batched whole-pair path with host buffers
         ofb_params p{w, h, levels, win, warp, 1.0f, batch};

@@ -217,15 +217,27 @@ int launch_inverse_f32(const float *sxx, const float *syy, const float *sxy, con
     return OFB_OK;
 }
 
-// Channel 0 of 3-channel interleaved u8 -> planar pitched u8.
+// Channel 0 of 3-channel interleaved u8 -> planar pitched u8.  VEC: four pixels per thread -- three aligned 32-bit loads
+// (12 source bytes), two byte permutes, one 32-bit store -- for widths that are multiples of 4 on 4-byte aligned
+// buffers; otherwise one pixel per thread.
+template <bool VEC>
 __global__ void __launch_bounds__(256)
 c3_to_planar_kernel(const uint8_t *__restrict__ src, int w, int h, uint8_t *__restrict__ dst, size_t dst_pitch,
                     size_t dst_stride)
 {
-    const int x = blockIdx.x * 256 + threadIdx.x, y = blockIdx.y;
+    const int x = (blockIdx.x * 256 + threadIdx.x) * (VEC ? 4 : 1), y = blockIdx.y;
     if (x >= w) return;
     const size_t img = blockIdx.z;
-    dst[img * dst_stride + (size_t)y * dst_pitch + x] = __ldg(src + (img * (size_t)w * h + (size_t)y * w + x) * 3);
+    const uint8_t *s = src + (img * (size_t)w * h + (size_t)y * w + x) * 3;
+    uint8_t *d = dst + img * dst_stride + (size_t)y * dst_pitch + x;
+    if (VEC) {
+        const uint32_t *s4 = reinterpret_cast<const uint32_t *>(s);
+        const uint32_t a = __ldg(s4), b = __ldg(s4 + 1), c = __ldg(s4 + 2); // bytes 0..11: channel 0 at 0, 3, 6, 9
+        const uint32_t lo = __byte_perm(a, b, 0x0630);                      // [a.b0, a.b3, b.b2, -]
+        *reinterpret_cast<uint32_t *>(d) = __byte_perm(lo, c, 0x5210);      // [.., .., .., c.b1]
+    } else {
+        *d = __ldg(s);
+    }
 }
 
 int launch_c3_to_planar(const uint8_t *src_c3, int w, int h, int n_images, uint8_t *dst, size_t dst_pitch,
@@ -235,8 +247,14 @@ int launch_c3_to_planar(const uint8_t *src_c3, int w, int h, int n_images, uint8
         set_error("c3_to_planar: bad geometry (w %d h %d images %d)", w, h, n_images);
         return OFB_ERR_INVALID;
     }
-    dim3 grid((unsigned)((w + 255) / 256), (unsigned)h, (unsigned)n_images);
-    c3_to_planar_kernel<<<grid, 256, 0, stream>>>(src_c3, w, h, dst, dst_pitch, dst_stride);
+    const bool vec = (w & 3) == 0 && ((reinterpret_cast<uintptr_t>(src_c3) | reinterpret_cast<uintptr_t>(dst) | dst_pitch | dst_stride) & 3) == 0;
+    if (vec) {
+        dim3 grid((unsigned)((w / 4 + 255) / 256), (unsigned)h, (unsigned)n_images);
+        c3_to_planar_kernel<true><<<grid, 256, 0, stream>>>(src_c3, w, h, dst, dst_pitch, dst_stride);
+    } else {
+        dim3 grid((unsigned)((w + 255) / 256), (unsigned)h, (unsigned)n_images);
+        c3_to_planar_kernel<false><<<grid, 256, 0, stream>>>(src_c3, w, h, dst, dst_pitch, dst_stride);
+    }
     OFB_CUDA_TRY(cudaGetLastError());
     if (launches) ++*launches;
     return OFB_OK;

@@ -58,6 +58,13 @@ inline ofb_ctx *default_context()
     }
     return ctx;
 }
+// The 2x2 solve of gpu::calc_opt_flow: OFB_SOLVE_EXACT (default, bit-identical to g_inv_matrix_float's double-precision
+// sequence) or OFB_SOLVE_FAST (tolerance mode: |du|,|dv| <= 1e-4 px + 1e-5 |ref| per level, ~15 % less kernel time).
+inline void set_lk_solve(int solve_mode)
+{
+    ofb_ctx *c = default_context();
+    if (c && ofb_ctx_set_solve(c, solve_mode) != OFB_OK) std::fprintf(stderr, "[ofb200] set_lk_solve: %s\n", ofb_last_error());
+}
 inline void report(const char *what, int rc)
 {
     last_status() = rc;

@@ -448,3 +448,19 @@ def test_fast_solve_whole_pipeline_close_to_exact(fast_ctx, oracle):
     assert (d > lim).mean() < 1e-3, f"{(d > lim).mean():.2e} of the total-flow values beyond the per-level tolerance"
     well = np.abs(ref[fin]) < 100.0  # ill-conditioned windows amplify any input change without bound
     assert d[well].max() < 0.25, f"max |d| {d[well].max():.3e}"
+
+
+@pytest.mark.parametrize("w,h", [(322, 246), (129, 65), (64, 48)])
+def test_flow_pairs_host_c3_layout_any_width(ctx, oracle, w, h):
+    """The 3-channel upload path (channel 0 -> planar): widths that are and are not multiples of 4 (vector / scalar
+    de-interleave), and the total-flow-only variant of the host call."""
+    levels, win = 2, 5
+    prevs = np.stack([oracle.make_frame(w, h, 0, 0, 4, 300 + i) for i in range(2)])
+    nexts = np.stack([oracle.make_frame(w, h, 0.75, -0.5 * i, 4, 300 + i) for i in range(2)])
+    got = ctx.flow_pairs_host(np.stack([oracle.to_c3(p) for p in prevs]), np.stack([oracle.to_c3(p) for p in nexts]), levels, win)
+    total = ctx.total_flow_pairs_host(prevs, nexts, levels, win)
+    for i in range(2):
+        ref, cums = oracle.flow_pair(prevs[i], nexts[i], levels, win, 2, oracle.SUMS_EXACT, 1.0, want_cum=True)
+        for k in range(levels):
+            assert_flow_identical(got[k][i], ref[k], f"{w}x{h} pair {i} level {k}")
+        assert_flow_identical(total[i], cums[0], f"{w}x{h} pair {i} total flow")
