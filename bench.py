@@ -666,7 +666,9 @@ def strips_block(env, ctx, w, h, levels, win, reps):
     K = 4  # handles = pairs that can be in flight at once
     handles = [NativeStrips(ctx, w, h, levels, win, world, rank, dev, WARP_BILINEAR, 1.0, 16, transport="peer") for _ in range(K)]
     ins = []
+    fused = os.environ.get("OFB_STRIPS_FUSED", "1") != "0"  # (experiments: the separate copy / wait kernels instead)
     for nat in handles:
+        nat.set_fused(fused)
         nat.set_total(False)
         y0, y1 = nat.own_rows(0)
         pin, nin = nat.input_rows()  # the producer writes the own rows where the runner keeps them
@@ -726,6 +728,8 @@ def strips_block(env, ctx, w, h, levels, win, reps):
         sum((hi - lo) * (w >> (k + 1)) * 8 for k in range(levels) for _, lo, hi, _ in plan.cum_messages(k, rank))
     rec = {"workload": f"{w}x{h} pair, {levels} levels, window {win}, row strips over {world} rank(s)", "n_ranks": world,
            "transport": "peer" if world > 1 else None, "reps": reps,
+           "halo_exchange": ("fused into the level kernels (peer stores + arrival flags from the producing kernel, flag waits in the "
+                             "consuming kernel)" if fused else "separate copy / wait kernels") if world > 1 else None,
            "algorithmic_bytes_per_pair": sum(level_bytes(w, h, k, levels, 1, 0 < k < levels - 1) for k in range(levels)) +
            2 * sum((w >> (k - 1)) * (h >> (k - 1)) + (w >> k) * (h >> k) for k in range(1, levels))}
     try:

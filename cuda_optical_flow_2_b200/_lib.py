@@ -89,6 +89,7 @@ SIGNATURES = {
     "ofb_strips_destroy": (C.c_int, [_vp]),
     "ofb_strips_input": (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_sz)]),
     "ofb_strips_set_total": (C.c_int, [_vp, C.c_int]),
+    "ofb_strips_set_fused": (C.c_int, [_vp, C.c_int]),
     "ofb_strips_peer_handle": (C.c_int, [_vp, _vp]),
     "ofb_strips_peer_connect": (C.c_int, [_vp, _vp]),
     "ofb_strips_peer_arena": (C.c_int, [_vp, C.POINTER(_vp)]),

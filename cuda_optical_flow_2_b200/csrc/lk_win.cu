@@ -2,6 +2,7 @@
 // (warp mode, cumulative output) dispatch.  See lk_level.cu for the entry point.
 #include "lk_level.cuh"
 
+#include <algorithm>
 #include <cstdlib>
 
 #ifndef LK_WIN
@@ -15,7 +16,7 @@ int lk_make_image_map(CUtensorMap *tm, const uint8_t *base, int w, int h, int n,
 int lk_make_flow_map(CUtensorMap *tm, const float *base, int w, int h, int n, size_t pair_stride_vec, int box_w, int box_rows,
                      int *usable);
 
-template <int WIN, int MODE, bool CUMOUT, bool FAST>
+template <int WIN, int MODE, bool CUMOUT, bool FAST, bool PEER>
 static int launch_one(const LkLevelArgs &a, cudaStream_t stream, unsigned long long *launches)
 {
     using C = LkCfg<WIN>;
@@ -23,7 +24,7 @@ static int launch_one(const LkLevelArgs &a, cudaStream_t stream, unsigned long l
     int dev = 0;
     OFB_CUDA_TRY(cudaGetDevice(&dev));
     if (dev < 64 && !attr_set[dev]) {
-        OFB_CUDA_TRY(cudaFuncSetAttribute(lk_level_kernel<WIN, MODE, CUMOUT, FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        OFB_CUDA_TRY(cudaFuncSetAttribute(lk_level_kernel<WIN, MODE, CUMOUT, FAST, PEER>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           C::smem_bytes(FAST, CUMOUT && MODE != 0)));
         attr_set[dev] = true;
     }
@@ -97,46 +98,76 @@ static int launch_one(const LkLevelArgs &a, cudaStream_t stream, unsigned long l
     p.flow_pair_stride = a.flow_pair_stride;
     p.reach_overflow = a.reach_overflow;
     p.cum_tma = cum_tma;
+    p.npush = a.npush;
+    p.nwait = a.nwait;
+    p.push_counter = a.push_counter;
+    p.epoch_src = a.epoch_src;
+    for (int d = 0; d < 2; d++) {
+        p.push[d] = LkPeerPush{};
+        p.wait[d] = LkPeerWait{};
+        if (d < a.npush) {
+            // CTAs of this launch that own rows of [row_lo, row_hi): every column strip of every row block that meets it
+            unsigned blocks = 0;
+            for (int b = 0; b < nby; b++) {
+                const int ys = a.out_y0 + b * rows_per_block, ye = std::min(ys + rows_per_block, a.out_y1);
+                if (ys < a.push[d].row_hi && ye > a.push[d].row_lo) blocks++;
+            }
+            p.push[d] = LkPeerPush{reinterpret_cast<float2 *>(a.push[d].dst), a.push[d].row_lo, a.push[d].row_hi, a.push[d].flag,
+                                   a.push[d].done, blocks * (unsigned)strips};
+            if (blocks == 0 || a.n_pairs != 1) {
+                set_error("lk_level: fused halo push needs one pair and rows inside the launch (rows [%d,%d))", a.push[d].row_lo,
+                          a.push[d].row_hi);
+                return OFB_ERR_INVALID;
+            }
+        }
+        if (d < a.nwait) p.wait[d] = LkPeerWait{a.wait[d].flag, a.wait[d].crow_lo, a.wait[d].crow_hi};
+    }
 
     dim3 grid((unsigned)strips, (unsigned)nby, (unsigned)a.n_pairs);
-    lk_level_kernel<WIN, MODE, CUMOUT, FAST><<<grid, LK_NT, C::smem_bytes(FAST, CUMOUT && MODE != 0), stream>>>(tmP, tmQ, tmC, p);
+    lk_level_kernel<WIN, MODE, CUMOUT, FAST, PEER><<<grid, LK_NT, C::smem_bytes(FAST, CUMOUT && MODE != 0), stream>>>(tmP, tmQ, tmC, p);
     OFB_CUDA_TRY(cudaGetLastError());
     if (launches) ++*launches;
     return OFB_OK;
 }
 
-template <int WIN, bool FAST> static int launch_lk_win_solve(const LkLevelArgs &a, cudaStream_t s, unsigned long long *l)
+template <int WIN, bool FAST, bool PEER> static int launch_lk_win_solve(const LkLevelArgs &a, cudaStream_t s, unsigned long long *l)
 {
     const bool co = a.cum_out != nullptr;
-    if (a.cum_in == nullptr) return co ? launch_one<WIN, 0, true, FAST>(a, s, l) : launch_one<WIN, 0, false, FAST>(a, s, l);
+    if (a.cum_in == nullptr)
+        return co ? launch_one<WIN, 0, true, FAST, PEER>(a, s, l) : launch_one<WIN, 0, false, FAST, false>(a, s, l);
     if (a.warp_mode == OFB_WARP_BILINEAR)
-        return co ? launch_one<WIN, 2, true, FAST>(a, s, l) : launch_one<WIN, 2, false, FAST>(a, s, l);
-    return co ? launch_one<WIN, 1, true, FAST>(a, s, l) : launch_one<WIN, 1, false, FAST>(a, s, l);
+        return co ? launch_one<WIN, 2, true, FAST, PEER>(a, s, l) : launch_one<WIN, 2, false, FAST, PEER>(a, s, l);
+    return co ? launch_one<WIN, 1, true, FAST, PEER>(a, s, l) : launch_one<WIN, 1, false, FAST, PEER>(a, s, l);
 }
 template <int WIN> int launch_lk_win(const LkLevelArgs &a, cudaStream_t s, unsigned long long *l)
 {
-    return a.solve_fast ? launch_lk_win_solve<WIN, true>(a, s, l) : launch_lk_win_solve<WIN, false>(a, s, l);
+    const bool peer = a.npush > 0 || a.nwait > 0;
+    if (peer) return a.solve_fast ? launch_lk_win_solve<WIN, true, true>(a, s, l) : launch_lk_win_solve<WIN, false, true>(a, s, l);
+    return a.solve_fast ? launch_lk_win_solve<WIN, true, false>(a, s, l) : launch_lk_win_solve<WIN, false, false>(a, s, l);
 }
 
 template int launch_lk_win<LK_WIN>(const LkLevelArgs &a, cudaStream_t s, unsigned long long *l);
 
 // Loads every variant of this window's kernel now (CUDA loads kernels lazily, and loading may synchronise the context:
 // a launch that first has to load its kernel can then not be enqueued behind a kernel that spins on a neighbour).
-template <int WIN, bool FAST> static int preload_lk_win_solve()
+template <int WIN, bool FAST, bool PEER> static int preload_lk_win_solve()
 {
     cudaFuncAttributes fa;
-    OFB_CUDA_TRY(cudaFuncGetAttributes(&fa, lk_level_kernel<WIN, 0, false, FAST>));
-    OFB_CUDA_TRY(cudaFuncGetAttributes(&fa, lk_level_kernel<WIN, 0, true, FAST>));
-    OFB_CUDA_TRY(cudaFuncGetAttributes(&fa, lk_level_kernel<WIN, 1, false, FAST>));
-    OFB_CUDA_TRY(cudaFuncGetAttributes(&fa, lk_level_kernel<WIN, 1, true, FAST>));
-    OFB_CUDA_TRY(cudaFuncGetAttributes(&fa, lk_level_kernel<WIN, 2, false, FAST>));
-    OFB_CUDA_TRY(cudaFuncGetAttributes(&fa, lk_level_kernel<WIN, 2, true, FAST>));
+    if (!PEER) OFB_CUDA_TRY(cudaFuncGetAttributes(&fa, lk_level_kernel<WIN, 0, false, FAST, false>));
+    OFB_CUDA_TRY(cudaFuncGetAttributes(&fa, lk_level_kernel<WIN, 0, true, FAST, PEER>));
+    OFB_CUDA_TRY(cudaFuncGetAttributes(&fa, lk_level_kernel<WIN, 1, false, FAST, PEER>));
+    OFB_CUDA_TRY(cudaFuncGetAttributes(&fa, lk_level_kernel<WIN, 1, true, FAST, PEER>));
+    OFB_CUDA_TRY(cudaFuncGetAttributes(&fa, lk_level_kernel<WIN, 2, false, FAST, PEER>));
+    OFB_CUDA_TRY(cudaFuncGetAttributes(&fa, lk_level_kernel<WIN, 2, true, FAST, PEER>));
     return OFB_OK;
 }
 template <int WIN> int preload_lk_win()
 {
-    const int rc = preload_lk_win_solve<WIN, false>();
-    return rc ? rc : preload_lk_win_solve<WIN, true>();
+    int rc = preload_lk_win_solve<WIN, false, false>();
+    if (!rc) rc = preload_lk_win_solve<WIN, true, false>();
+    if (!rc) rc = preload_lk_win_solve<WIN, false, true>();
+    if (!rc) rc = preload_lk_win_solve<WIN, true, true>();
+    return rc;
 }
 template int preload_lk_win<LK_WIN>();
 

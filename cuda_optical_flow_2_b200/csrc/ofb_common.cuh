@@ -70,6 +70,21 @@ struct LkLevelArgs {
     int *reach_overflow;   // optional device flag: a warp sample fell outside the local rows
     int sm_count;
     int solve_fast;        // OFB_SOLVE_FAST: tolerance-mode solve (lk_solve4_fast) instead of the bit-exact one
+    // row strips, halo exchange fused into the kernel (strips.cu; zero = off)
+    struct PeerPush {
+        float *dst;            // neighbour's coarser-flow buffer, offset so that dst + 2*o is the peer's copy of this level's pixel o
+        int row_lo, row_hi;    // local rows the neighbour needs
+        unsigned *flag;        // arrival flag in the neighbour's memory
+        const unsigned *done;  // in this rank's memory
+    } push[2];
+    int npush;
+    struct PeerWait {
+        const unsigned *flag;  // arrival flag in this rank's memory
+        int crow_lo, crow_hi;  // local rows of cum_in the neighbour provides
+    } wait[2];
+    int nwait;
+    unsigned *push_counter;    // [2], zero between launches
+    const unsigned *epoch_src;
 };
 int launch_lk_level(const LkLevelArgs &a, cudaStream_t stream, unsigned long long *launches);
 int preload_lk_level(int win); // loads the window's kernels now instead of at their first launch

@@ -148,7 +148,9 @@ struct ArenaLayout {
     //                   done[src] at L * world + src = last epoch rank src finished reading what this rank pushed;
     //                   counter[x] at (L + 1) * world + x: blocks of this rank's push kernel that have finished (local);
     //                   pairs at (L + 1) * world + L: pairs this rank has completed (local).  The epoch of a pair is
-    //                   pairs + 1, read from here by the kernels, so that a captured CUDA graph of one pair replays.
+    //                   pairs + 1, read from here by the kernels, so that a captured CUDA graph of one pair replays;
+    //                   fused[2 * x + d] after that: CTAs of the level kernel that have pushed their rows of exchange x to
+    //                   target d (local; the halo push fused into the level kernels).
 };
 static ArenaLayout arena_layout(const StripPlan &pl, int rank)
 {
@@ -164,7 +166,7 @@ static ArenaLayout arena_layout(const StripPlan &pl, int rank)
     a.prev0 = take(pitch0 * (v[0].eb1 - v[0].eb0));
     a.next0 = take(pitch0 * (v[0].eb1 - v[0].eb0));
     for (int k = 0; k < pl.levels; k++) a.cum_in[k] = take((size_t)(v[k].w >> 1) * std::max(v[k].cy1 - v[k].cy0, 1) * 8);
-    a.flags = take(((size_t)(pl.levels + 1) * pl.world + pl.levels + 1) * sizeof(unsigned));
+    a.flags = take(((size_t)(pl.levels + 1) * pl.world + pl.levels + 1 + 2 * (size_t)pl.levels) * sizeof(unsigned));
     a.bytes = off;
     return a;
 }
@@ -298,6 +300,7 @@ struct ofb_strips {
     std::vector<float *> cum_dst;              // where level k's kernel writes its cumulative flow (buffer-row indexing like
                                                // flow[k]): straight into cum_in[k-1], whose rows [cy0, cy1) contain the own rows
     int want_total = 1;                        // level 0 also writes its cumulative flow (the total flow of the pair)
+    int fused = 1;                             // peer-memory transport: cumulative-flow halo rows are pushed by the level kernels themselves
     int *overflow = nullptr;
     std::vector<void *> allocs;
     // peer-memory transport
@@ -771,6 +774,18 @@ int ofb_strips_set_total(ofb_strips *st, int on)
     return OFB_OK;
 }
 
+// Whether the cumulative-flow halo rows are pushed by the level kernels themselves (default) or by separate copy / wait
+// kernels (peer-memory transport; for comparison).
+int ofb_strips_set_fused(ofb_strips *st, int on)
+{
+    if (!st) {
+        set_error("strips_set_fused: NULL handle");
+        return OFB_ERR_INVALID;
+    }
+    st->fused = on ? 1 : 0;
+    return OFB_OK;
+}
+
 // One pair: own rows of level 0 in, residual (and cumulative) flow of the own rows of every level out, all
 // asynchronous on `stream`.  prev_own_d / next_own_d: rows [y0, y1) of level 0, planar u8 with `pitch` bytes per row.
 //
@@ -870,8 +885,14 @@ static int strips_run_impl(ofb_strips *st, const uint8_t *prev_own_d, const uint
         if (rc) return rc;
     }
     // coarse to fine: rows [cy0, cy1) of cum_{k+1} into cum_in[k] (own part copied, the rest received), then the level
+    bool pushed_by_kernel = false; // the exchange that feeds the level at hand was pushed by the previous (coarser) level's kernel
     for (int k = L - 1; k >= 0; k--) {
         const LevelStrip &s = st->s[k];
+        struct WaitSrc {
+            int peer, crow_lo, crow_hi;
+        } wait_src[2] = {};
+        int nwait = 0;
+        bool wait_in_kernel = false;
         if (k < L - 1) {
             const LevelStrip &up = st->s[k + 1];
             // level k+1 wrote its own rows of cum_{k+1} straight into cum_in[k] (cum_dst); the neighbours' rows follow
@@ -903,11 +924,44 @@ static int strips_run_impl(ofb_strips *st, const uint8_t *prev_own_d, const uint
                     if (overlap(pu.y0, pu.y1, s.cy0, s.cy1, &lo, &hi)) { // the peer's cum rows I need
                         sources.push_back(peer);
                         add_unique(all_sources, peer);
+                        if (nwait < 2) wait_src[nwait] = {peer, lo - s.cy0, hi - s.cy0};
+                        nwait++;
                     }
                 }
                 const int x = L - 1 - k; // exchanges 1 .. L-1
-                int rc = peer_exchange(st, x, sends, sources, q, launches, on(2 * x), on(2 * x + 1));
+                // Fused form: level k+1's kernel has already pushed my rows (pushed_by_kernel, previous iteration) and this
+                // level's kernel waits for the neighbours' flags itself; the copy / wait kernels remain for what does not
+                // fit the kernel's two slots (strips thinner than the halo).
+                wait_in_kernel = st->fused && nwait >= 1 && nwait <= 2;
+                int rc = peer_exchange(st, x, sends, sources, q, launches, on(2 * x) && !pushed_by_kernel, on(2 * x + 1) && !wait_in_kernel);
                 if (rc) return rc;
+            }
+        }
+        // what THIS level's kernel pushes: my rows of cum_k that the neighbours' level k-1 needs (exchange L-k)
+        LkLevelArgs::PeerPush push[2] = {};
+        int npush = 0;
+        pushed_by_kernel = false;
+        if (peer_mode && st->fused && k >= 1) {
+            int cnt = 0, lo, hi;
+            for (int peer = 0; peer < pl.world; peer++) {
+                if (peer == me) continue;
+                const LevelStrip pf = pl.level(k - 1, peer); // the peer's finer level reads rows [cy0, cy1) of cum_k
+                if (!overlap(s.y0, s.y1, pf.cy0, pf.cy1, &lo, &hi)) continue;
+                if (cnt < 2 && st->peer_arena[peer]) {
+                    const int xn = L - k;
+                    push[cnt].dst = reinterpret_cast<float *>(st->peer_arena[peer] + st->peer_lay[peer].cum_in[k - 1]) +
+                                    ((ptrdiff_t)s.eb0 - pf.cy0) * (ptrdiff_t)s.w * 2;
+                    push[cnt].row_lo = lo - s.eb0;
+                    push[cnt].row_hi = hi - s.eb0;
+                    push[cnt].flag = flag_ptr(st->peer_arena[peer], st->peer_lay[peer], (size_t)xn * pl.world + me);
+                    push[cnt].done = flag_ptr(st->arena, st->lay, (size_t)L * pl.world + peer);
+                    if (std::find(st->done_from.begin(), st->done_from.end(), peer) == st->done_from.end()) st->done_from.push_back(peer);
+                }
+                cnt++;
+            }
+            if (cnt >= 1 && cnt <= 2) {
+                npush = cnt;
+                pushed_by_kernel = true;
             }
         }
         if (!on(2 * (L - 1 - k) + 1)) continue;
@@ -939,6 +993,19 @@ static int strips_run_impl(ofb_strips *st, const uint8_t *prev_own_d, const uint
         a.reach_overflow = st->overflow;
         a.sm_count = ctx_sm_count(st->ctx);
         a.solve_fast = ctx_solve_fast(st->ctx);
+        if (npush > 0 && a.cum_out) {
+            a.npush = npush;
+            a.push[0] = push[0];
+            a.push[1] = push[1];
+            a.push_counter = flag_ptr(st->arena, st->lay, (size_t)(L + 1) * pl.world + L + 1 + 2 * (size_t)(L - k));
+        }
+        if (wait_in_kernel) {
+            a.nwait = nwait;
+            const int x = L - 1 - k;
+            for (int d = 0; d < nwait; d++)
+                a.wait[d] = {flag_ptr(st->arena, st->lay, (size_t)x * pl.world + wait_src[d].peer), wait_src[d].crow_lo, wait_src[d].crow_hi};
+        }
+        a.epoch_src = flag_ptr(st->arena, st->lay, (size_t)(L + 1) * pl.world + L);
         int rc = launch_lk_level(a, q, launches);
         if (rc) return rc;
     }

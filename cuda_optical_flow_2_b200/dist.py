@@ -441,6 +441,11 @@ class NativeStrips:
     def set_total(self, on: bool) -> None:
         self.L.check(self.lib.ofb_strips_set_total(self._h, 1 if on else 0))
 
+    def set_fused(self, on: bool) -> None:
+        """Peer-memory transport: cumulative-flow halo rows pushed by the level kernels themselves (default) or by
+        separate copy / wait kernels."""
+        self.L.check(self.lib.ofb_strips_set_fused(self._h, 1 if on else 0))
+
     def arena(self) -> int:
         p = self.C.c_void_p()
         self.L.check(self.lib.ofb_strips_peer_arena(self._h, self.C.byref(p)))

@@ -266,6 +266,7 @@ int ofb_strips_check(ofb_strips *s, void *stream, int *overflow);
 int ofb_strips_destroy(ofb_strips *s);
 int ofb_strips_input(const ofb_strips *s, uint8_t **prev_own_d, uint8_t **next_own_d, size_t *pitch);
 int ofb_strips_set_total(ofb_strips *s, int on);
+int ofb_strips_set_fused(ofb_strips *s, int on); /* peer memory: halo rows pushed by the level kernels themselves (default on) */
 int ofb_strips_peer_handle(ofb_strips *s, void *blob128);
 int ofb_strips_peer_connect(ofb_strips *s, const void *blobs_world_x_128);
 int ofb_strips_peer_arena(ofb_strips *s, void **arena_d);
