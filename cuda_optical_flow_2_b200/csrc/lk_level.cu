@@ -3,9 +3,19 @@
 // translation unit (lk_win.cu, compiled once per -DLK_WIN=n) so that the build runs in parallel.
 #include "lk_level.cuh"
 
+#include <cstdlib>
 #include <mutex>
 
 namespace ofb {
+
+bool pdl_enabled()
+{
+    static const bool on = [] {
+        const char *e = getenv("OFB_PDL"); // off by default: measured on B200 it does not pay (ofb_common.cuh)
+        return e && e[0] == '1';
+    }();
+    return on;
+}
 
 PFN_encodeTiled get_encode_tiled()
 {

@@ -124,8 +124,8 @@ static int launch_one(const LkLevelArgs &a, cudaStream_t stream, unsigned long l
     }
 
     dim3 grid((unsigned)strips, (unsigned)nby, (unsigned)a.n_pairs);
-    lk_level_kernel<WIN, MODE, CUMOUT, FAST, PEER><<<grid, LK_NT, C::smem_bytes(FAST, CUMOUT && MODE != 0), stream>>>(tmP, tmQ, tmC, p);
-    OFB_CUDA_TRY(cudaGetLastError());
+    OFB_CUDA_TRY(launch_pdl(lk_level_kernel<WIN, MODE, CUMOUT, FAST, PEER>, grid, dim3(LK_NT), C::smem_bytes(FAST, CUMOUT && MODE != 0),
+                            stream, tmP, tmQ, tmC, p));
     if (launches) ++*launches;
     return OFB_OK;
 }

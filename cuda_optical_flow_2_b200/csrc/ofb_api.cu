@@ -3,6 +3,7 @@
 
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -23,7 +24,7 @@ static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; 
 
 } // namespace ofb
 
-#define OFB_LANES 3
+#define OFB_LANES 6 /* streams available to the batched host entry point; it uses c->lanes of them */
 
 // One growable device workspace per context; carved by offset for each call.  Growing it frees the
 // old block (cudaFree synchronises the device), so steady-state calls allocate nothing -- unlike
@@ -31,6 +32,8 @@ static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; 
 struct ofb_ctx {
     int device = 0;
     int sm_count = 0;
+    int lanes = 3;      // sub-batches in flight in ofb_flow_pairs_host (developer override: OFB_E2E_LANES)
+    int sub_pairs = 0;  // pairs per sub-batch there; 0 = chosen from the batch size (developer override: OFB_E2E_SUB)
     int solve_fast = 0; // OFB_SOLVE_*: which 2x2 solve the fused level kernel runs (ofb_ctx_set_solve)
     cudaStream_t stream = nullptr; // used by the synchronous host-pointer entry points
     cudaStream_t lane_stream[OFB_LANES] = {}; // the batched host entry point pipelines sub-batches over these
@@ -321,6 +324,11 @@ int ofb_ctx_create(int device, ofb_ctx **out)
     }
     c->device = device;
     c->sm_count = prop.multiProcessorCount;
+    if (const char *e = getenv("OFB_E2E_LANES")) { // developer overrides for experiments
+        const int v = atoi(e);
+        if (v >= 1 && v <= OFB_LANES) c->lanes = v;
+    }
+    if (const char *e = getenv("OFB_E2E_SUB")) c->sub_pairs = atoi(e) > 0 ? atoi(e) : 0;
     e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) {
         set_error("cudaStreamCreate failed: %s", cudaGetErrorString(e));
@@ -863,9 +871,11 @@ static int flow_pairs_host_impl(ofb_ctx *c, const ofb_params *p, const unsigned 
     // Sub-batches are kept small (at least eight per lane when the batch allows): the first upload and the last
     // download are the part of the pipeline nothing overlaps, and a 1080p pair already is 12 MB in and 22 MB out.
     const int n = p->n_pairs;
-    int sub = n / (8 * OFB_LANES);
+    const int LANES = c->lanes;
+    int sub = n / (8 * LANES);
     if (sub < 1) sub = 1;
     if (sub > 8) sub = 8;
+    if (c->sub_pairs > 0) sub = c->sub_pairs < n ? c->sub_pairs : n;
     ofb_params ps = *p;
     ps.n_pairs = sub;
     const size_t pitch0 = align_up((size_t)p->w, 64), istride0 = pitch0 * (size_t)p->h;
@@ -885,12 +895,12 @@ static int flow_pairs_host_impl(ofb_ctx *c, const ofb_params *p, const unsigned 
         plan_pairs(&ps, &pl, &cv2);
         lane_bytes = align_up(plan_base + pl.bytes, 256);
     }
-    rc = ws_reserve(c, lane_bytes * OFB_LANES);
+    rc = ws_reserve(c, lane_bytes * LANES);
     if (rc) return rc;
-    for (int lane = 0; lane < OFB_LANES; lane++)
+    for (int lane = 0; lane < LANES; lane++)
         if ((rc = ws_acquire(c, c->lane_stream[lane]))) return rc;
     for (int first = 0, sb = 0; first < n; first += sub, sb++) {
-        const int lane = sb % OFB_LANES;
+        const int lane = sb % LANES;
         const int cnt = (n - first < sub) ? n - first : sub;
         cudaStream_t st = c->lane_stream[lane];
         uint8_t *B = c->ws + lane_bytes * lane;
@@ -928,7 +938,7 @@ static int flow_pairs_host_impl(ofb_ctx *c, const ofb_params *p, const unsigned 
                                          cudaMemcpyDeviceToHost, st));
         }
     }
-    for (int lane = 0; lane < OFB_LANES; lane++) OFB_CUDA_TRY(cudaStreamSynchronize(c->lane_stream[lane]));
+    for (int lane = 0; lane < LANES; lane++) OFB_CUDA_TRY(cudaStreamSynchronize(c->lane_stream[lane]));
     return OFB_OK;
 }
 

@@ -43,6 +43,35 @@ struct DeviceGuard {
     }
 };
 
+// ---- programmatic dependent launch (sm_90+) ------------------------------------------------------------------------------
+// The kernels of a pair form a dependent chain (pyramid steps, then the levels coarse to fine), and for one pair or one
+// strip each of them is short: launched this way a kernel may be scheduled while its predecessor in the stream is still
+// draining -- its launch latency and prologue overlap the predecessor's tail -- and waits with pdl_wait() (before its first
+// global-memory access) until the predecessor has completed and its memory is visible.  Every kernel launched through
+// launch_pdl MUST call pdl_wait().  OFF by default (OFB_PDL=1 in the environment turns it on): measured on B200 the eager
+// single-pair latency does not move (49.9 us either way), a replayed CUDA graph of one pair gets slower (43 -> 51 us) and so
+// do row strips with several pairs in flight (0.247 -> 0.259 ms): early-scheduled CTAs hold SM slots while they wait.
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#endif
+
 // ---- fused LK level (lk_level.cu) ----------------------------------------------------------
 struct LkLevelArgs {
     const uint8_t *prev;   // planar u8, local rows [0, h_local)

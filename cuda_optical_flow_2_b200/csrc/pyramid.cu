@@ -32,6 +32,8 @@ pyr_down_planar_kernel(const uint8_t *__restrict__ src, size_t src_pitch, size_t
                        uint8_t *__restrict__ dst, size_t dst_pitch, size_t dst_stride, int src_y_off, int dst_y0,
                        int src_rows, const uint8_t *__restrict__ src2, uint8_t *__restrict__ dst2, int n_first)
 {
+    pdl_launch_dependents(); // (programmatic dependent launch, ofb_common.cuh)
+    pdl_wait();
     // images n_first .. of the launch form a second batch with its own base pointers (prev and next frames of the
     // pairs in one launch)
     const int zi = (int)blockIdx.z < n_first ? (int)blockIdx.z : (int)blockIdx.z - n_first;
@@ -136,9 +138,8 @@ int launch_pyr_down_strip(const uint8_t *src, size_t src_pitch, int sw, int src_
         return OFB_ERR_INVALID;
     }
     dim3 grid((unsigned)((dw + 255) / 256), (unsigned)((dh + 15) / 16), (unsigned)n_images);
-    pyr_down_planar_kernel<<<grid, block, 0, stream>>>(src, src_pitch, src_stride, dw, dh, dst, dst_pitch, dst_stride, src_y_off,
-                                                       dst_y0, src_rows, nullptr, nullptr, n_images);
-    OFB_CUDA_TRY(cudaGetLastError());
+    OFB_CUDA_TRY(launch_pdl(pyr_down_planar_kernel, grid, block, 0, stream, src, src_pitch, src_stride, dw, dh, dst, dst_pitch, dst_stride,
+                            src_y_off, dst_y0, src_rows, (const uint8_t *)nullptr, (uint8_t *)nullptr, n_images));
     if (launches) ++*launches;
     return OFB_OK;
 }
@@ -169,9 +170,8 @@ int launch_pyr_down(const uint8_t *src, size_t src_pitch, size_t src_stride, int
         }
         dim3 block(32, 8);
         dim3 grid((unsigned)((dw + 255) / 256), (unsigned)((dh + 15) / 16), (unsigned)nz);
-        pyr_down_planar_kernel<<<grid, block, 0, stream>>>(src, src_pitch, src_stride, dw, dh, dst, dst_pitch, dst_stride, 0, 0,
-                                                           sh, src2, dst2, n_images);
-        OFB_CUDA_TRY(cudaGetLastError());
+        OFB_CUDA_TRY(launch_pdl(pyr_down_planar_kernel, grid, block, 0, stream, src, src_pitch, src_stride, dw, dh, dst, dst_pitch,
+                                dst_stride, 0, 0, sh, src2, dst2, n_images));
         if (launches) ++*launches;
     } else {
         for (int i = 0; i < n_images; i++) {
