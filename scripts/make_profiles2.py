@@ -46,7 +46,7 @@ def summaries(rep):
 
         grid = [int(x) for x in re.findall(r"\d+", d["Grid Size"])] if "Grid Size" in d else None
         name = d["Kernel Name"]
-        m = re.search(r"lk_level_kernel<(?:\(int\))?(\d+), (?:\(int\))?(\d+), (?:\(bool\))?(\d), (?:\(bool\))?(\d)>", name)
+        m = re.search(r"lk_level_kernel<(?:\(int\))?(\d+), (?:\(int\))?(\d+), (?:\(bool\))?(\d), (?:\(bool\))?(\d)(?:, (?:\(bool\))?\d)?>", name)
         dur = val("gpu__time_duration.sum") / {"ns": 1e6, "us": 1e3, "ms": 1.0, "msecond": 1.0, "usecond": 1e3, "nsecond": 1e6}.get(u["gpu__time_duration.sum"], 1e6)
         sh = val("l1tex__data_pipe_lsu_wavefronts_mem_shared.sum")
         tot = val("l1tex__data_pipe_lsu_wavefronts.sum") if "l1tex__data_pipe_lsu_wavefronts.sum" in d else None
@@ -70,8 +70,9 @@ def summaries(rep):
     return res
 
 
-PAIRS, W, H = 256, 1920, 1080
+W, H = 1920, 1080
 levels = summaries(rep)
+PAIRS = int(re.findall(r"\d+", levels[0]["grid"])[2])  # grid.z = pairs per launch
 for s in levels:
     if s["template"]:
         mode, cumout = int(s["template"][1]), int(s["template"][2])
@@ -95,9 +96,9 @@ l0 = [s for s in levels if s.get("level") == 0][0]
 j = dict(l0)
 j["dram_bytes_per_launch"] = l0["dram_bytes_read"] + l0["dram_bytes_write"]
 j["note"] = ("ncu --set full --clock-control none of the level-0 launch (lk_level_kernel<9, bilinear, no cumulative out, fast solve>) of "
-             "`python bench.py --quick --steps 2 --warmup 3 --no-cpu-baseline` (256 pairs of 1080p per launch). DRAM bytes / algorithmic "
+             "`python bench.py --quick --steps 2 --warmup 3 --no-cpu-baseline` (%d pairs of 1080p per launch). DRAM bytes / algorithmic "
              "bytes = %.3f: no wasted re-reads; the excess is halo rows/columns and the margin of the staged window of next, most of "
-             "which L2 absorbs." % l0["dram_bytes_over_algorithmic"])
+             "which L2 absorbs." % (PAIRS, l0["dram_bytes_over_algorithmic"]))
 json.dump(j, open(os.path.join(out, "ncu_traffic.json"), "w"), indent=1)
 
 # SASS evidence per variant of the 9x9 window
@@ -106,7 +107,7 @@ sass = subprocess.run(["cuobjdump", "-sass", obj], capture_output=True, text=Tru
 pat = re.compile(r"UTMALDG|SYNCS|STG\.E\.ENL2\.256|I2F\.F64|I2F\.S64|MUFU\.RCP64H|MUFU\.RCP\b|IMAD\.WIDE\b|DFMA|DMUL|LDS\.128|BAR\.SYNC")
 with open(os.path.join(out, f"{tag}_sass_excerpt.txt"), "w") as f:
     f.write("cuobjdump -sass cuda_optical_flow_2_b200/csrc/lk_win_9.o | grep -E '" + pat.pattern + "' -- counts per kernel variant\n"
-            "(template arguments: window, warp mode 0 none / 1 nearest / 2 bilinear, cumulative out, fast solve)\n\n")
+            "(template arguments: window, warp mode 0 none / 1 nearest / 2 bilinear, cumulative out, fast solve, fused halo exchange)\n\n")
     cur, counts = None, {}
     for line in sass.splitlines():
         m = re.search(r"Function : (\S+)", line)
@@ -118,12 +119,12 @@ with open(os.path.join(out, f"{tag}_sass_excerpt.txt"), "w") as f:
             for k in pat.findall(line):
                 counts[cur][k] = counts[cur].get(k, 0) + 1
     for fn, c in counts.items():
-        m = re.search(r"ILi(\d+)ELi(\d)ELb(\d)ELb(\d)E", fn)
-        label = f"lk_level_kernel<{m.group(1)},{m.group(2)},{m.group(3)},{m.group(4)}>" if m else fn
+        m = re.search(r"ILi(\d+)ELi(\d)ELb(\d)ELb(\d)ELb(\d)E", fn)
+        label = f"lk_level_kernel<{m.group(1)},{m.group(2)},{m.group(3)},{m.group(4)},{m.group(5)}>" if m else fn
         f.write(f"{label:34s} " + "  ".join(f"{k} {v}" for k, v in sorted(c.items())) + "\n")
     # a few literal lines of the bilinear fast kernel: the TMA loads, the mbarrier wait, a 256-bit store, the conversions
-    f.write("\nliteral lines, lk_level_kernel<9,2,0,1>:\n")
-    fn = "_ZN3ofb15lk_level_kernelILi9ELi2ELb0ELb1EEEv14CUtensorMap_stS1_S1_NS_14LkKernelParamsE"
+    f.write("\nliteral lines, lk_level_kernel<9,2,0,1,0>:\n")
+    fn = "_ZN3ofb15lk_level_kernelILi9ELi2ELb0ELb1ELb0EEEv14CUtensorMap_stS1_S1_NS_14LkKernelParamsE"
     one = subprocess.run(["cuobjdump", "-sass", "-fun", fn, obj], capture_output=True, text=True).stdout
     seen = set()
     for line in one.splitlines():
