@@ -44,3 +44,32 @@ def test_b200_arm_has_no_cpu_fallback():
     r = run_bench("--steps", "1")
     assert r.returncode != 0
     assert "no CPU fallback" in json.loads(r.stdout.strip().splitlines()[-1])["error"]
+
+
+def test_algorithmic_bytes_match_the_survey_figures():
+    """the per-unit figures the roofline is quoted on.  configs[1]: 43,027,200 B per 1080p pair (level-0
+    kernel alone 24,883,200 B); configs[0]: 3,072,000 B; configs[2]: 179,884,800 B; configs[4] with 4 levels: 719,539,200 B."""
+    sys.path.insert(0, ROOT)
+    import bench
+
+    def pair_bytes(w, h, levels):
+        lk = sum(bench.level_bytes(w, h, k, levels, 1, 0 < k < levels - 1) for k in range(levels))
+        pyr = 2 * sum((w >> (k - 1)) * (h >> (k - 1)) + (w >> k) * (h >> k) for k in range(1, levels))
+        return lk + pyr
+
+    assert bench.level_bytes(1920, 1080, 0, 3, 1, False) == 24_883_200
+    assert pair_bytes(1920, 1080, 3) == 43_027_200
+    assert pair_bytes(640, 480, 1) == 3_072_000
+    assert pair_bytes(3840, 2160, 4) == 179_884_800
+    assert pair_bytes(7680, 4320, 4) == 719_539_200
+
+
+def test_both_arms_print_the_same_config():
+    """The driver compares the arms' `config`: it is one constant, and everything run-specific lives under `run`."""
+    sys.path.insert(0, ROOT)
+    import bench
+
+    assert set(bench.CONFIG) == {"workload"} and "1920x1080" in bench.CONFIG["workload"]
+    r = run_bench("--impl", "reference", "--steps", "1", "--warmup", "0")
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert line["config"] == bench.CONFIG and "pairs_per_step" in line["run"]
