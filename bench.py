@@ -837,19 +837,35 @@ def main_b200(args):
 
     if world == 1 and not args.quick:
         refgpu = refgpu_block()  # (a child process; after every measurement of this arm)
+    composing = os.environ.get("OFB_NO_COMPOSE", "0") != "1"
     if rank == 0:
         n0 = W * H
         r0 = roofline_of(lvl_ms[0], W, H, 0, LEVELS, B, False, peak)
         traffic = ncu_traffic()
         total_ms = ms_step * args.steps
-        roofline = {"bound": "hbm", "kernel": f"lk_level_kernel<9, bilinear, {args.solve} solve> level 0", "achieved": r0["achieved"],
-                    "peak": peak, "unit": "GB/s", "frac": r0["frac"], "peak_source": peak_src,
-                    "algorithmic_bytes_per_launch": r0["algorithmic_bytes_per_launch"], "avg_launch_ms": r0["avg_launch_ms"],
+        # Level 1 does not write its cumulative flow: level 0 composes it from the residual flows of levels 1 and 2 (even
+        # sizes, per-pixel warp: csrc/ofb_api.cu run_pairs_device; OFB_NO_COMPOSE=1 restores the old form).  The level-0
+        # kernel then also reads the level-2 flow: 8 B per level-2 pixel = 0.5 B per level-0 pixel on top of SURVEY 8(d)'s 12.
+        n2 = (W >> 2) * (H >> 2)
+        own_bytes = r0["algorithmic_bytes_per_launch"] + (B * n2 * 8 if composing else 0)
+        own_ach = own_bytes / (r0["avg_launch_ms"] * 1e-3) / 1e9 if r0["avg_launch_ms"] > 0 else 0.0
+        pair_survey, pair_moved = 43027200, 43027200 - (8 * (W >> 1) * (H >> 1) - 8 * n2 if composing else 0)
+        roofline = {"bound": "hbm", "kernel": f"lk_level_kernel<9, bilinear, {args.solve} solve{', composing' if composing else ''}> level 0",
+                    "achieved": own_ach, "peak": peak, "unit": "GB/s", "frac": own_ach / peak, "peak_source": peak_src,
+                    "algorithmic_bytes_per_launch": own_bytes, "avg_launch_ms": r0["avg_launch_ms"],
+                    "bytes_note": ("every array once: 1 B prev + 1 B next + 8 B flow out per pixel, 8 B per level-1 pixel of coarser flow in"
+                                   + (", 8 B per level-2 pixel of the flow it composes with (12.5 B/px; level 1 in turn writes no cumulative "
+                                      "flow, 8 B per level-1 pixel less)" if composing else " (12 B/px)")),
+                    "frac_at_survey_12_bytes_per_px": r0["frac"],
                     "traffic": (traffic or {}).get("dram_bytes_per_launch"),
                     "traffic_note": (traffic or {}).get("note"),
-                    "other_levels": {"level_1_with_cumulative_out": roofline_of(lvl_ms[1], W, H, 1, LEVELS, B, True, peak),
+                    "other_levels": {"level_1": dict(roofline_of(lvl_ms[1], W, H, 1, LEVELS, B, not composing, peak),
+                                                     writes_cumulative_flow=not composing),
                                      "level_2_coarsest": roofline_of(lvl_ms[2], W, H, 2, LEVELS, B, False, peak)},
-                    "whole_step_frac": B * 43027200 / (ms_step * 1e-3) / 1e9 / peak,
+                    "whole_step_frac": B * pair_survey / (ms_step * 1e-3) / 1e9 / peak,
+                    "whole_step_frac_bytes_moved": B * pair_moved / (ms_step * 1e-3) / 1e9 / peak,
+                    "whole_step_note": f"{pair_survey} B per pair by SURVEY 8(d) (the definition of the work); {pair_moved} B with the "
+                                       "composition (no level-1 cumulative flow written, the level-2 flow read once more)",
                     "step_share": {"pyramid": pyr_ms[0] / total_ms if total_ms else None,
                                    **{f"lk_level_{k}": lvl_ms[k][0] / total_ms for k in range(LEVELS)}}}
         other_name = "exact" if args.solve == "fast" else "fast"

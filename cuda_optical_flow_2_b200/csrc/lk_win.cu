@@ -16,7 +16,7 @@ int lk_make_image_map(CUtensorMap *tm, const uint8_t *base, int w, int h, int n,
 int lk_make_flow_map(CUtensorMap *tm, const float *base, int w, int h, int n, size_t pair_stride_vec, int box_w, int box_rows,
                      int *usable);
 
-template <int WIN, int MODE, bool CUMOUT, bool FAST, bool PEER>
+template <int WIN, int MODE, bool CUMOUT, bool FAST, bool PEER, bool COMP>
 static int launch_one(const LkLevelArgs &a, cudaStream_t stream, unsigned long long *launches)
 {
     using C = LkCfg<WIN>;
@@ -24,7 +24,7 @@ static int launch_one(const LkLevelArgs &a, cudaStream_t stream, unsigned long l
     int dev = 0;
     OFB_CUDA_TRY(cudaGetDevice(&dev));
     if (dev < 64 && !attr_set[dev]) {
-        OFB_CUDA_TRY(cudaFuncSetAttribute(lk_level_kernel<WIN, MODE, CUMOUT, FAST, PEER>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        OFB_CUDA_TRY(cudaFuncSetAttribute(lk_level_kernel<WIN, MODE, CUMOUT, FAST, PEER, COMP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           C::smem_bytes(FAST, CUMOUT && MODE != 0)));
         attr_set[dev] = true;
     }
@@ -41,6 +41,18 @@ static int launch_one(const LkLevelArgs &a, cudaStream_t stream, unsigned long l
     if (MODE != 0) {
         rc = lk_make_flow_map(&tmC, a.cum_in, a.cum_w, a.cum_h_local, a.n_pairs, a.cum_pair_stride, LK_CTW, C::NBR, &cum_tma);
         if (rc) return rc;
+    }
+
+    CUtensorMap tmC2 = tmP;
+    if (COMP) {
+        int usable = 0;
+        rc = lk_make_flow_map(&tmC2, a.cum2_in, a.cum_w >> 1, a.cum_h_global >> 1, a.n_pairs, a.cum2_pair_stride, LK_C2W, C::NBR / 2 + 1,
+                              &usable);
+        if (rc) return rc;
+        if (!usable || !cum_tma) {
+            set_error("lk_level: composition on the fly needs 16-byte aligned coarser flow rows (caller checks lk_can_compose)");
+            return OFB_ERR_INVALID;
+        }
     }
 
     const int out_rows = a.out_y1 - a.out_y0;
@@ -98,6 +110,9 @@ static int launch_one(const LkLevelArgs &a, cudaStream_t stream, unsigned long l
     p.flow_pair_stride = a.flow_pair_stride;
     p.reach_overflow = a.reach_overflow;
     p.cum_tma = cum_tma;
+    p.cum2_in = reinterpret_cast<const float2 *>(a.cum2_in);
+    p.cum2_w = a.cum_w >> 1;
+    p.cum2_pair_stride = a.cum2_pair_stride;
     p.npush = a.npush;
     p.nwait = a.nwait;
     p.push_counter = a.push_counter;
@@ -124,8 +139,8 @@ static int launch_one(const LkLevelArgs &a, cudaStream_t stream, unsigned long l
     }
 
     dim3 grid((unsigned)strips, (unsigned)nby, (unsigned)a.n_pairs);
-    OFB_CUDA_TRY(launch_pdl(lk_level_kernel<WIN, MODE, CUMOUT, FAST, PEER>, grid, dim3(LK_NT), C::smem_bytes(FAST, CUMOUT && MODE != 0),
-                            stream, tmP, tmQ, tmC, p));
+    OFB_CUDA_TRY(launch_pdl(lk_level_kernel<WIN, MODE, CUMOUT, FAST, PEER, COMP>, grid, dim3(LK_NT), C::smem_bytes(FAST, CUMOUT && MODE != 0),
+                            stream, tmP, tmQ, tmC, tmC2, p));
     if (launches) ++*launches;
     return OFB_OK;
 }
@@ -134,10 +149,15 @@ template <int WIN, bool FAST, bool PEER> static int launch_lk_win_solve(const Lk
 {
     const bool co = a.cum_out != nullptr;
     if (a.cum_in == nullptr)
-        return co ? launch_one<WIN, 0, true, FAST, PEER>(a, s, l) : launch_one<WIN, 0, false, FAST, false>(a, s, l);
+        return co ? launch_one<WIN, 0, true, FAST, PEER, false>(a, s, l) : launch_one<WIN, 0, false, FAST, false, false>(a, s, l);
+    if (!PEER && a.cum2_in != nullptr) { // the coarser level's cumulative flow composed on the fly
+        if (a.warp_mode == OFB_WARP_BILINEAR)
+            return co ? launch_one<WIN, 2, true, FAST, false, true>(a, s, l) : launch_one<WIN, 2, false, FAST, false, true>(a, s, l);
+        return co ? launch_one<WIN, 1, true, FAST, false, true>(a, s, l) : launch_one<WIN, 1, false, FAST, false, true>(a, s, l);
+    }
     if (a.warp_mode == OFB_WARP_BILINEAR)
-        return co ? launch_one<WIN, 2, true, FAST, PEER>(a, s, l) : launch_one<WIN, 2, false, FAST, PEER>(a, s, l);
-    return co ? launch_one<WIN, 1, true, FAST, PEER>(a, s, l) : launch_one<WIN, 1, false, FAST, PEER>(a, s, l);
+        return co ? launch_one<WIN, 2, true, FAST, PEER, false>(a, s, l) : launch_one<WIN, 2, false, FAST, PEER, false>(a, s, l);
+    return co ? launch_one<WIN, 1, true, FAST, PEER, false>(a, s, l) : launch_one<WIN, 1, false, FAST, PEER, false>(a, s, l);
 }
 template <int WIN> int launch_lk_win(const LkLevelArgs &a, cudaStream_t s, unsigned long long *l)
 {
@@ -153,12 +173,18 @@ template int launch_lk_win<LK_WIN>(const LkLevelArgs &a, cudaStream_t s, unsigne
 template <int WIN, bool FAST, bool PEER> static int preload_lk_win_solve()
 {
     cudaFuncAttributes fa;
-    if (!PEER) OFB_CUDA_TRY(cudaFuncGetAttributes(&fa, lk_level_kernel<WIN, 0, false, FAST, false>));
-    OFB_CUDA_TRY(cudaFuncGetAttributes(&fa, lk_level_kernel<WIN, 0, true, FAST, PEER>));
-    OFB_CUDA_TRY(cudaFuncGetAttributes(&fa, lk_level_kernel<WIN, 1, false, FAST, PEER>));
-    OFB_CUDA_TRY(cudaFuncGetAttributes(&fa, lk_level_kernel<WIN, 1, true, FAST, PEER>));
-    OFB_CUDA_TRY(cudaFuncGetAttributes(&fa, lk_level_kernel<WIN, 2, false, FAST, PEER>));
-    OFB_CUDA_TRY(cudaFuncGetAttributes(&fa, lk_level_kernel<WIN, 2, true, FAST, PEER>));
+    if (!PEER) OFB_CUDA_TRY(cudaFuncGetAttributes(&fa, lk_level_kernel<WIN, 0, false, FAST, false, false>));
+    OFB_CUDA_TRY(cudaFuncGetAttributes(&fa, lk_level_kernel<WIN, 0, true, FAST, PEER, false>));
+    OFB_CUDA_TRY(cudaFuncGetAttributes(&fa, lk_level_kernel<WIN, 1, false, FAST, PEER, false>));
+    OFB_CUDA_TRY(cudaFuncGetAttributes(&fa, lk_level_kernel<WIN, 1, true, FAST, PEER, false>));
+    OFB_CUDA_TRY(cudaFuncGetAttributes(&fa, lk_level_kernel<WIN, 2, false, FAST, PEER, false>));
+    OFB_CUDA_TRY(cudaFuncGetAttributes(&fa, lk_level_kernel<WIN, 2, true, FAST, PEER, false>));
+    if (!PEER) {
+        OFB_CUDA_TRY(cudaFuncGetAttributes(&fa, lk_level_kernel<WIN, 1, false, FAST, false, true>));
+        OFB_CUDA_TRY(cudaFuncGetAttributes(&fa, lk_level_kernel<WIN, 1, true, FAST, false, true>));
+        OFB_CUDA_TRY(cudaFuncGetAttributes(&fa, lk_level_kernel<WIN, 2, false, FAST, false, true>));
+        OFB_CUDA_TRY(cudaFuncGetAttributes(&fa, lk_level_kernel<WIN, 2, true, FAST, false, true>));
+    }
     return OFB_OK;
 }
 template <int WIN> int preload_lk_win()

@@ -229,6 +229,27 @@ static int run_pairs_device(ofb_ctx *c, const ofb_params *p, const PairPlan &pl,
         int rc = prof_end(c, st);
         if (rc) return rc;
     }
+    // Which warped levels materialise their cumulative flow.  Level j (1 <= j <= L-2) need not when the next finer level can
+    // compose it on the fly from flow_j and cum_{j+1} (lk_level_kernel<..., COMP>): 8 bytes per pixel less to write at level
+    // j, whose kernel is bound by exactly those stores.  Composition needs even sizes (no clamped coarse indices), TMA-able
+    // rows, the per-pixel warp modes, and the parent's cumulative flow to exist -- so at most every other level skips.
+    bool mat[OFB_MAX_LEVELS] = {}, comp[OFB_MAX_LEVELS] = {};
+    mat[L - 1] = true;
+    static const bool allow_compose = [] {
+        const char *e = getenv("OFB_NO_COMPOSE"); // developer switch for A/B measurements
+        return !(e && e[0] == '1');
+    }();
+    for (int j = L - 2; j >= 1; j--) {
+        const int kr = j - 1; // the reader
+        const bool even = !((pl.w[kr] | pl.h[kr] | pl.w[j] | pl.h[j] | pl.w[j + 1]) & 1);
+        const float *c2 = (j + 1 == L - 1) ? flow_levels[j + 1] : reinterpret_cast<const float *>(base + pl.off_cum[j + 1]);
+        const bool aligned = !((reinterpret_cast<uintptr_t>(flow_levels[j]) | reinterpret_cast<uintptr_t>(c2)) & 15);
+        if (allow_compose && mat[j + 1] && even && aligned && p->warp_mode != OFB_WARP_AS_WRITTEN) {
+            comp[kr] = true;
+        } else {
+            mat[j] = true;
+        }
+    }
     for (int k = L - 1; k >= 0; k--) {
         LkLevelArgs a{};
         a.prev = pp[k];
@@ -250,16 +271,21 @@ static int run_pairs_device(ofb_ctx *c, const ofb_params *p, const PairPlan &pl,
         a.sm_count = c->sm_count;
         a.solve_fast = c->solve_fast;
         if (k < L - 1) {
-            // cum_{k+1}: the coarsest level's cumulative flow is its residual flow
-            a.cum_in = (k + 1 == L - 1) ? flow_levels[k + 1] : reinterpret_cast<const float *>(base + pl.off_cum[k + 1]);
+            // cum_{k+1}: the coarsest level's cumulative flow is its residual flow; a level that did not materialise its
+            // own hands over its residual flow together with its parent's cumulative flow
+            a.cum_in = (k + 1 == L - 1 || comp[k]) ? flow_levels[k + 1] : reinterpret_cast<const float *>(base + pl.off_cum[k + 1]);
             a.cum_w = pl.w[k + 1];
             a.cum_h_global = pl.h[k + 1];
             a.cum_y_off = 0;
             a.cum_h_local = pl.h[k + 1];
             a.cum_pair_stride = (size_t)pl.w[k + 1] * pl.h[k + 1];
+            if (comp[k]) {
+                a.cum2_in = (k + 2 == L - 1) ? flow_levels[k + 2] : reinterpret_cast<const float *>(base + pl.off_cum[k + 2]);
+                a.cum2_pair_stride = (size_t)pl.w[k + 2] * pl.h[k + 2];
+            }
         }
         if (k == 0) a.cum_out = total_flow;
-        else if (k <= L - 2) a.cum_out = reinterpret_cast<float *>(base + pl.off_cum[k]);
+        else if (k <= L - 2 && mat[k]) a.cum_out = reinterpret_cast<float *>(base + pl.off_cum[k]);
         int rc = prof_begin(c, k, st);
         if (rc) return rc;
         rc = launch_lk_level(a, st, &c->launches);

@@ -93,6 +93,10 @@ struct LkLevelArgs {
     int cum_y_off;         // global coarse row of cum_in's row 0
     int cum_h_local;       // rows held by cum_in
     size_t cum_pair_stride;   // float2 elements between pairs
+    // Composition on the fly (whole frames): cum_in is the RESIDUAL flow of the next-coarser level and cum2_in the cumulative
+    // flow of the level above that ((cum_w >> 1) x (cum_h_global >> 1) per pair); NULL = cum_in is the cumulative flow itself
+    const float *cum2_in;
+    size_t cum2_pair_stride;  // float2 elements between pairs
     float *flow_out;       // float2, local rows (same origin as prev/next)
     float *cum_out;        // optional
     size_t flow_pair_stride;  // float2 elements between pairs (flow_out and cum_out)

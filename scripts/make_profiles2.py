@@ -46,7 +46,7 @@ def summaries(rep):
 
         grid = [int(x) for x in re.findall(r"\d+", d["Grid Size"])] if "Grid Size" in d else None
         name = d["Kernel Name"]
-        m = re.search(r"lk_level_kernel<(?:\(int\))?(\d+), (?:\(int\))?(\d+), (?:\(bool\))?(\d), (?:\(bool\))?(\d)(?:, (?:\(bool\))?\d)?>", name)
+        m = re.search(r"lk_level_kernel<(?:\(int\))?(\d+), (?:\(int\))?(\d+), (?:\(bool\))?(\d), (?:\(bool\))?(\d)(?:, (?:\(bool\))?\d)*>", name)
         dur = val("gpu__time_duration.sum") / {"ns": 1e6, "us": 1e3, "ms": 1.0, "msecond": 1.0, "usecond": 1e3, "nsecond": 1e6}.get(u["gpu__time_duration.sum"], 1e6)
         sh = val("l1tex__data_pipe_lsu_wavefronts_mem_shared.sum")
         tot = val("l1tex__data_pipe_lsu_wavefronts.sum") if "l1tex__data_pipe_lsu_wavefronts.sum" in d else None
@@ -77,9 +77,13 @@ for s in levels:
     if s["template"]:
         mode, cumout = int(s["template"][1]), int(s["template"][2])
         # which pyramid level: coarsest = unwarped; level 1 = warped + cumulative out; level 0 = warped
-        lvl = 2 if mode == 0 else (1 if cumout else 0)
+        gx = int(re.findall(r"\d+", s["grid"])[0])  # column strips: 16 at level 0, 8 at level 1, 4 at level 2 (1080p)
+        lvl = {16: 0, 8: 1, 4: 2}[gx]
         px = PAIRS * (W >> lvl) * (H >> lvl)
-        alg = px * 10 + (0 if mode == 0 else PAIRS * (W >> (lvl + 1)) * (H >> (lvl + 1)) * 8) + (px * 8 if cumout else 0)
+        targs = re.findall(r"\d+", s["kernel"].split("<")[1].split(">")[0])
+        composing = len(targs) >= 6 and targs[5] == "1"
+        alg = px * 10 + (0 if mode == 0 else PAIRS * (W >> (lvl + 1)) * (H >> (lvl + 1)) * 8) + (px * 8 if cumout else 0) + \
+            (PAIRS * (W >> (lvl + 2)) * (H >> (lvl + 2)) * 8 if composing else 0)
         s.update({"level": lvl, "pixels": px, "algorithmic_bytes_per_launch": alg,
                   "dram_bytes_over_algorithmic": (s["dram_bytes_read"] + s["dram_bytes_write"]) / alg,
                   "thread_inst_per_pixel": float(s["warp_inst_executed"].replace(",", "")) * 32 / px,
@@ -107,7 +111,7 @@ sass = subprocess.run(["cuobjdump", "-sass", obj], capture_output=True, text=Tru
 pat = re.compile(r"UTMALDG|SYNCS|STG\.E\.ENL2\.256|I2F\.F64|I2F\.S64|MUFU\.RCP64H|MUFU\.RCP\b|IMAD\.WIDE\b|DFMA|DMUL|LDS\.128|BAR\.SYNC")
 with open(os.path.join(out, f"{tag}_sass_excerpt.txt"), "w") as f:
     f.write("cuobjdump -sass cuda_optical_flow_2_b200/csrc/lk_win_9.o | grep -E '" + pat.pattern + "' -- counts per kernel variant\n"
-            "(template arguments: window, warp mode 0 none / 1 nearest / 2 bilinear, cumulative out, fast solve, fused halo exchange)\n\n")
+            "(template arguments: window, warp mode 0 none / 1 nearest / 2 bilinear, cumulative out, fast solve, fused halo exchange, composing)\n\n")
     cur, counts = None, {}
     for line in sass.splitlines():
         m = re.search(r"Function : (\S+)", line)
@@ -119,12 +123,12 @@ with open(os.path.join(out, f"{tag}_sass_excerpt.txt"), "w") as f:
             for k in pat.findall(line):
                 counts[cur][k] = counts[cur].get(k, 0) + 1
     for fn, c in counts.items():
-        m = re.search(r"ILi(\d+)ELi(\d)ELb(\d)ELb(\d)ELb(\d)E", fn)
-        label = f"lk_level_kernel<{m.group(1)},{m.group(2)},{m.group(3)},{m.group(4)},{m.group(5)}>" if m else fn
+        m = re.search(r"ILi(\d+)ELi(\d)ELb(\d)ELb(\d)ELb(\d)ELb(\d)E", fn)
+        label = f"lk_level_kernel<{m.group(1)},{m.group(2)},{m.group(3)},{m.group(4)},{m.group(5)},{m.group(6)}>" if m else fn
         f.write(f"{label:34s} " + "  ".join(f"{k} {v}" for k, v in sorted(c.items())) + "\n")
     # a few literal lines of the bilinear fast kernel: the TMA loads, the mbarrier wait, a 256-bit store, the conversions
-    f.write("\nliteral lines, lk_level_kernel<9,2,0,1,0>:\n")
-    fn = "_ZN3ofb15lk_level_kernelILi9ELi2ELb0ELb1ELb0EEEv14CUtensorMap_stS1_S1_NS_14LkKernelParamsE"
+    f.write("\nliteral lines, lk_level_kernel<9,2,0,1,0,1>:\n")
+    fn = "_ZN3ofb15lk_level_kernelILi9ELi2ELb0ELb1ELb0ELb1EEEv14CUtensorMap_stS1_S1_S1_NS_14LkKernelParamsE"
     one = subprocess.run(["cuobjdump", "-sass", "-fun", fn, obj], capture_output=True, text=True).stdout
     seen = set()
     for line in one.splitlines():
