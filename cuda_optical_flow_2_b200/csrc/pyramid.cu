@@ -27,6 +27,9 @@ __device__ __forceinline__ void pyr_hrow(const uint4 q, uint32_t left, uint32_t 
     }
 }
 
+#ifndef PYR_ROWS
+#define PYR_ROWS 2 // output rows per thread
+#endif
 __global__ void __launch_bounds__(256)
 pyr_down_planar_kernel(const uint8_t *__restrict__ src, size_t src_pitch, size_t src_stride, int dw, int dh,
                        uint8_t *__restrict__ dst, size_t dst_pitch, size_t dst_stride, int src_y_off, int dst_y0,
@@ -43,17 +46,17 @@ pyr_down_planar_kernel(const uint8_t *__restrict__ src, size_t src_pitch, size_t
     }
     const int tx = blockIdx.x * 32 + threadIdx.x;
     const int x0 = 8 * tx;
-    const int y = 2 * (blockIdx.y * 8 + threadIdx.y);
+    constexpr int NR = PYR_ROWS;
+    const int y = NR * (blockIdx.y * 8 + threadIdx.y);
     // whole warps stay alive for the shuffle; lanes past the row only skip their loads and stores
     const bool live = x0 < dw && y < dh;
     const uint8_t *s = src + (size_t)zi * src_stride;
-    const bool two = y + 1 < dh;
-    uint32_t h[5][4];
+    uint32_t h[2 * NR + 1][4];
 #pragma unroll
-    for (int r = 0; r < 5; r++) {
+    for (int r = 0; r < 2 * NR + 1; r++) {
         const int sg = 2 * (dst_y0 + y) - 1 + r; // global source row; above the image: skipped
         const int sy = sg - src_y_off;
-        const bool ok = live && sg >= 0 && sy < src_rows && (r < 3 || two);
+        const bool ok = live && sg >= 0 && sy < src_rows && (r < 3 || y + (r - 1) / 2 < dh);
         uint4 q = make_uint4(0, 0, 0, 0);
         if (ok) q = __ldg(reinterpret_cast<const uint4 *>(s + (size_t)sy * src_pitch + 2 * x0));
         uint32_t left = __shfl_up_sync(0xffffffffu, q.w >> 24, 1);
@@ -62,8 +65,8 @@ pyr_down_planar_kernel(const uint8_t *__restrict__ src, size_t src_pitch, size_t
     }
     if (!live) return;
 #pragma unroll
-    for (int o = 0; o < 2; o++) {
-        if (o == 1 && !two) break;
+    for (int o = 0; o < NR; o++) {
+        if (y + o >= dh) break;
         uint32_t v[4];
 #pragma unroll
         for (int i = 0; i < 4; i++) v[i] = ((h[2 * o][i] + 2 * h[2 * o + 1][i] + h[2 * o + 2][i]) >> 4) & 0x00ff00ffu;
@@ -137,7 +140,7 @@ int launch_pyr_down_strip(const uint8_t *src, size_t src_pitch, int sw, int src_
         set_error("pyr_down_strip: bad image count / strides");
         return OFB_ERR_INVALID;
     }
-    dim3 grid((unsigned)((dw + 255) / 256), (unsigned)((dh + 15) / 16), (unsigned)n_images);
+    dim3 grid((unsigned)((dw + 255) / 256), (unsigned)((dh + 8 * PYR_ROWS - 1) / (8 * PYR_ROWS)), (unsigned)n_images);
     OFB_CUDA_TRY(launch_pdl(pyr_down_planar_kernel, grid, block, 0, stream, src, src_pitch, src_stride, dw, dh, dst, dst_pitch, dst_stride,
                             src_y_off, dst_y0, src_rows, (const uint8_t *)nullptr, (uint8_t *)nullptr, n_images));
     if (launches) ++*launches;
@@ -169,7 +172,7 @@ int launch_pyr_down(const uint8_t *src, size_t src_pitch, size_t src_stride, int
             return OFB_ERR_INVALID;
         }
         dim3 block(32, 8);
-        dim3 grid((unsigned)((dw + 255) / 256), (unsigned)((dh + 15) / 16), (unsigned)nz);
+        dim3 grid((unsigned)((dw + 255) / 256), (unsigned)((dh + 8 * PYR_ROWS - 1) / (8 * PYR_ROWS)), (unsigned)nz);
         OFB_CUDA_TRY(launch_pdl(pyr_down_planar_kernel, grid, block, 0, stream, src, src_pitch, src_stride, dw, dh, dst, dst_pitch,
                                 dst_stride, 0, 0, sh, src2, dst2, n_images));
         if (launches) ++*launches;
