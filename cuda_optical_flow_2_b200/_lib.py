@@ -54,6 +54,7 @@ SIGNATURES = {
     "ofb_ctx_profile_read": (C.c_int, [_vp, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_ulonglong)]),
     "ofb_flow_pairs_device": (C.c_int, [_vp, C.POINTER(OfbParams), _vp, _vp, _sz, _sz, C.POINTER(_vp), _vp, _vp]),
     "ofb_pyr_down_device": (C.c_int, [_vp, _vp, _sz, _sz, C.c_int, C.c_int, _vp, _sz, _sz, C.c_int, _vp]),
+    "ofb_pyr_down2_device": (C.c_int, [_vp, _vp, _sz, _sz, C.c_int, C.c_int, _vp, _sz, _sz, _vp, _sz, _sz, C.c_int, _vp]),
     "ofb_pyr_down_strip_device": (C.c_int, [_vp, _vp, _sz, C.c_int, C.c_int, C.c_int, _vp, _sz, C.c_int, C.c_int, _vp]),
     "ofb_lk_level_device": (C.c_int, [_vp, _vp, _vp, _sz, _sz, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float,
                                       _vp, _vp, _vp, _vp]),

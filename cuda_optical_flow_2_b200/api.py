@@ -332,6 +332,18 @@ class Context:
                                               C.c_void_p(stream)))
         return dst
 
+    def pyr_down2_device(self, src, sw: int, stream: int = 0):
+        """Two pyramid steps in one launch: src (n, sh, pitch) -> (dst1 (n, sh>>1, pitch1), dst2 (n, sh>>2, pitch2))."""
+        import torch
+
+        n, sh, sp = src.shape
+        d1 = torch.zeros((n, sh >> 1, align_up(sw >> 1, 64)), dtype=torch.uint8, device=src.device)
+        d2 = torch.zeros((n, sh >> 2, align_up(sw >> 2, 64)), dtype=torch.uint8, device=src.device)
+        L.check(self._lib.ofb_pyr_down2_device(self._h, src.data_ptr(), sp, sp * sh, sw, sh, d1.data_ptr(), d1.shape[2],
+                                               d1.shape[2] * d1.shape[1], d2.data_ptr(), d2.shape[2], d2.shape[2] * d2.shape[1],
+                                               n, C.c_void_p(stream)))
+        return d1, d2
+
     def pyr_down_strip_device(self, src, sw: int, src_y_off: int, dst, dst_y0: int, dst_y1: int, stream: int = 0):
         """Row-strip pyramid step: src (rows, pitch) holds global rows from src_y_off; dst (dst_y1-dst_y0, pitch_d)."""
         L.check(self._lib.ofb_pyr_down_strip_device(self._h, src.data_ptr(), src.stride(0), sw, src.shape[0], src_y_off,

@@ -158,6 +158,16 @@ struct PairPlan {
     size_t bytes = 0;
 };
 
+// Two pyramid steps per launch (pyramid.cu: pyr_roll_kernel<true>); OFB_PYR_FUSE=0 builds level by level (A/B measurements).
+static bool pyr_fuse_enabled()
+{
+    static const bool on = [] {
+        const char *e = getenv("OFB_PYR_FUSE");
+        return !(e && e[0] == '0');
+    }();
+    return on;
+}
+
 static void plan_pairs(const ofb_params *p, PairPlan *pl, Carver *cv)
 {
     pl->L = p->levels;
@@ -213,17 +223,21 @@ static int run_pairs_device(ofb_ctx *c, const ofb_params *p, const PairPlan &pl,
         pn[k] = base + pl.off_next[k];
         pitch[k] = pl.pitch[k];
         istr[k] = pl.istride[k];
-        // both frames of every pair in one launch
-        const bool one = 2 * n <= 65535; // grid.z limit
-        int rc = launch_pyr_down(pp[k - 1], pitch[k - 1], istr[k - 1], pl.w[k - 1], pl.h[k - 1],
-                                 const_cast<uint8_t *>(pp[k]), pitch[k], istr[k], n, 1, st, &c->launches, one ? pn[k - 1] : nullptr,
-                                 one ? const_cast<uint8_t *>(pn[k]) : nullptr);
-        if (rc) return rc;
-        if (!one) {
-            rc = launch_pyr_down(pn[k - 1], pitch[k - 1], istr[k - 1], pl.w[k - 1], pl.h[k - 1], const_cast<uint8_t *>(pn[k]),
-                                 pitch[k], istr[k], n, 1, st, &c->launches);
+    }
+    const bool one = 2 * n <= 65535; // grid.z limit: both frames of every pair in one launch
+    for (int k = 1; k < L;) {
+        // two pyramid steps per launch where two are left (level k is then never read back), else one
+        const bool two = pyr_fuse_enabled() && k + 1 < L;
+        for (int f = 0; f < (one ? 1 : 2); f++) {
+            const uint8_t *const *src = f ? pn : pp;
+            int rc = launch_pyr_roll(src[k - 1], pitch[k - 1], istr[k - 1], pl.w[k - 1], pl.h[k - 1], const_cast<uint8_t *>(src[k]),
+                                     pitch[k], istr[k], two ? const_cast<uint8_t *>(src[k + 1]) : nullptr, two ? pitch[k + 1] : 0,
+                                     two ? istr[k + 1] : 0, n, st, &c->launches, one ? pn[k - 1] : nullptr,
+                                     one ? const_cast<uint8_t *>(pn[k]) : nullptr,
+                                     one && two ? const_cast<uint8_t *>(pn[k + 1]) : nullptr, c->sm_count);
             if (rc) return rc;
         }
+        k += two ? 2 : 1;
     }
     if (L > 1) {
         int rc = prof_end(c, st);
@@ -555,6 +569,21 @@ int ofb_pyr_down_device(ofb_ctx *c, const uint8_t *src_d, size_t src_pitch, size
     OFB_GUARD(c);
     return launch_pyr_down(src_d, src_pitch, src_image_stride, sw, sh, dst_d, dst_pitch, dst_image_stride, n_images, 1,
                            static_cast<cudaStream_t>(stream), &c->launches);
+}
+
+int ofb_pyr_down2_device(ofb_ctx *c, const uint8_t *src_d, size_t src_pitch, size_t src_image_stride, int sw, int sh,
+                         uint8_t *dst1_d, size_t dst1_pitch, size_t dst1_image_stride, uint8_t *dst2_d, size_t dst2_pitch,
+                         size_t dst2_image_stride, int n_images, void *stream)
+{
+    OFB_CHECK_CTX(c);
+    if (!src_d || !dst1_d || !dst2_d) {
+        set_error("NULL image pointer");
+        return OFB_ERR_INVALID;
+    }
+    OFB_GUARD(c);
+    return launch_pyr_roll(src_d, src_pitch, src_image_stride, sw, sh, dst1_d, dst1_pitch, dst1_image_stride, dst2_d, dst2_pitch,
+                           dst2_image_stride, n_images, static_cast<cudaStream_t>(stream), &c->launches, nullptr, nullptr, nullptr,
+                           c->sm_count);
 }
 
 int ofb_pyr_down_strip_device(ofb_ctx *c, const uint8_t *src_d, size_t src_pitch, int sw, int src_rows, int src_y_off,
@@ -1357,10 +1386,15 @@ int ofb_stream_push_bgr_host(ofb_stream *s, const unsigned char *frame_bgr, floa
                               s->sig_b, reinterpret_cast<double *>(B + s->off_lut), lvl0, s->pitch[0], st, &c->launches);
         if (rc) return rc;
     }
-    for (int k = 1; k < p.levels; k++) { // main.cu:250
-        rc = launch_pyr_down(B + s->off_pyr[cur][k - 1], s->pitch[k - 1], 0, p.w >> (k - 1), p.h >> (k - 1),
-                             B + s->off_pyr[cur][k], s->pitch[k], 0, 1, 1, st, &c->launches);
+    for (int k = 1; k < p.levels;) { // main.cu:250; two steps per launch where two are left
+        const bool two = pyr_fuse_enabled() && k + 1 < p.levels;
+        rc = launch_pyr_roll(B + s->off_pyr[cur][k - 1], s->pitch[k - 1], s->pitch[k - 1] * (size_t)(p.h >> (k - 1)), p.w >> (k - 1),
+                             p.h >> (k - 1), B + s->off_pyr[cur][k], s->pitch[k], s->pitch[k] * (size_t)(p.h >> k),
+                             two ? B + s->off_pyr[cur][k + 1] : nullptr, two ? s->pitch[k + 1] : 0,
+                             two ? s->pitch[k + 1] * (size_t)(p.h >> (k + 1)) : 0, 1, st, &c->launches, nullptr, nullptr, nullptr,
+                             c->sm_count);
         if (rc) return rc;
+        k += two ? 2 : 1;
     }
     if (s->frames > 0) {
         for (int k = p.levels - 1; k >= 0; k--) { // main.cu:256-262

@@ -128,6 +128,11 @@ int launch_pyr_down(const uint8_t *src, size_t src_pitch, size_t src_stride, int
                     size_t dst_pitch, size_t dst_stride, int n_images, int channels, cudaStream_t stream,
                     unsigned long long *launches, const uint8_t *src2 = nullptr, uint8_t *dst2 = nullptr);
 
+int launch_pyr_roll(const uint8_t *src, size_t src_pitch, size_t src_stride, int sw, int sh, uint8_t *dst1, size_t pitch1,
+                    size_t stride1, uint8_t *dst2, size_t pitch2, size_t stride2, int n_images, cudaStream_t stream,
+                    unsigned long long *launches, const uint8_t *srcB = nullptr, uint8_t *dst1B = nullptr,
+                    uint8_t *dst2B = nullptr, int sm_count = 0);
+
 int launch_pyr_down_strip(const uint8_t *src, size_t src_pitch, int sw, int src_rows, int src_y_off, uint8_t *dst,
                           size_t dst_pitch, int dst_y0, int dst_y1, cudaStream_t stream, unsigned long long *launches,
                           int n_images = 1, size_t src_stride = 0, size_t dst_stride = 0);

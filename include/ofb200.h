@@ -104,6 +104,14 @@ int ofb_flow_pairs_device(ofb_ctx *ctx, const ofb_params *p, const uint8_t *prev
 int ofb_pyr_down_device(ofb_ctx *ctx, const uint8_t *src_d, size_t src_pitch, size_t src_image_stride, int sw, int sh,
                         uint8_t *dst_d, size_t dst_pitch, size_t dst_image_stride, int n_images, void *stream);
 
+/* Two pyramid steps in one launch: dst1 = (sw>>1) x (sh>>1) and dst2 = (sw>>2) x (sh>>2), byte-identical to two
+ * ofb_pyr_down_device calls (gpu::gauss_pyramid's loop over levels, OptFlowGpu.cu:1262-1290), but level +1 is not read
+ * back from memory: the kernel forms level +2 from the bytes it has just produced.  What the batch entry points use
+ * while at least two levels are left to build. */
+int ofb_pyr_down2_device(ofb_ctx *ctx, const uint8_t *src_d, size_t src_pitch, size_t src_image_stride, int sw, int sh,
+                         uint8_t *dst1_d, size_t dst1_pitch, size_t dst1_image_stride, uint8_t *dst2_d, size_t dst2_pitch,
+                         size_t dst2_image_stride, int n_images, void *stream);
+
 /* Row-strip variant of ofb_pyr_down_device for frames partitioned across GPUs: the source buffer
  * holds global rows [src_y_off, src_y_off + src_rows) of a level of width sw; destination rows
  * [dst_y0, dst_y1) (global numbering) of the next level are written to dst_d, whose row 0 is

@@ -23,12 +23,12 @@ build)
 run)
     pairs=${2:-256}; reps=${3:-10}
     echo "== baseline (in-tree library)"
-    python scripts/prof_pairs.py "$pairs" "$reps" | head -3
+    python scripts/prof_pairs.py "$pairs" "$reps" | head -4
     for d in scratch/variants/*/; do
         [ -f "$d/libofb200.so" ] || continue
         echo "== $(basename "$d"): $(cat "$d/flags.txt")"
         OFB200_LIB="$PWD/$d/libofb200.so" python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1 | cut -c1-120
-        OFB200_LIB="$PWD/$d/libofb200.so" python scripts/prof_pairs.py "$pairs" "$reps" | head -3
+        OFB200_LIB="$PWD/$d/libofb200.so" python scripts/prof_pairs.py "$pairs" "$reps" | head -4
     done
     ;;
 *) echo "usage: $0 build <tag> \"<flags>\" | run [pairs] [reps]"; exit 2;;

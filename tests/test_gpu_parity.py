@@ -66,6 +66,39 @@ def test_pyr_down_device_byte_exact(ctx, oracle, w, h):
         assert np.array_equal(got[i], oracle.pyr_down(imgs[i])), f"image {i}"
 
 
+@pytest.mark.parametrize("w,h", [(640, 480), (1920, 1080), (101, 77), (64, 34), (258, 130), (2000, 70), (36, 300), (4, 4)])
+def test_pyr_down2_device_byte_exact(ctx, oracle, w, h):
+    """Two pyramid steps in one launch (level +2 formed from the level +1 bytes still in registers) = two oracle steps."""
+    torch = _torch()
+    from cuda_optical_flow_2_b200 import planar_to_device
+
+    imgs = np.stack([oracle.make_frame(w, h, 0, 0, 4, 200 + i) for i in range(3)])
+    d1, d2 = ctx.pyr_down2_device(planar_to_device(imgs), w)
+    torch.cuda.synchronize()
+    g1, g2 = d1.cpu().numpy()[:, :, : w >> 1], d2.cpu().numpy()[:, :, : w >> 2]
+    for i in range(3):
+        r1 = oracle.pyr_down(imgs[i])
+        assert np.array_equal(g1[i], r1), f"image {i} level +1"
+        assert np.array_equal(g2[i], oracle.pyr_down(r1)), f"image {i} level +2"
+
+
+@pytest.mark.parametrize("rows", [1, 3, 37])
+def test_pyr_down_single_image_many_row_groups(ctx, oracle, rows):
+    """One small image: the launcher shortens the row groups (down to 2 rows per thread) to fill the GPU."""
+    torch = _torch()
+    from cuda_optical_flow_2_b200 import planar_to_device
+
+    w, h = 520, 4 * rows + 2
+    img = oracle.make_frame(w, h, 0, 0, 4, 300 + rows)[None]
+    d = ctx.pyr_down_device(planar_to_device(img), w)
+    d1, d2 = ctx.pyr_down2_device(planar_to_device(img), w)
+    torch.cuda.synchronize()
+    r1 = oracle.pyr_down(img[0])
+    assert np.array_equal(d.cpu().numpy()[0, :, : w >> 1], r1)
+    assert np.array_equal(d1.cpu().numpy()[0, :, : w >> 1], r1)
+    assert np.array_equal(d2.cpu().numpy()[0, :, : w >> 2], oracle.pyr_down(r1))
+
+
 # ------------------------------------------------------------------------------------ single level
 @pytest.mark.parametrize("w,h,win", [(640, 480, 5), (640, 480, 9), (320, 240, 19), (203, 117, 15), (64, 64, 3),
                                      (131, 59, 7), (250, 40, 11), (96, 200, 13), (128, 128, 17), (1920, 1080, 9)])
