@@ -49,6 +49,9 @@ SIGNATURES = {
     "ofb_ctx_reserve_pairs": (C.c_int, [_vp, C.POINTER(OfbParams)]),
     "ofb_ctx_set_solve": (C.c_int, [_vp, C.c_int]),
     "ofb_ctx_get_solve": (C.c_int, [_vp, i32p]),
+    "ofb_ctx_set_host_threads": (C.c_int, [_vp, C.c_int]),
+    "ofb_ctx_get_host_threads": (C.c_int, [_vp, i32p]),
+    "ofb_c3_extract_host": (C.c_int, [_vp, _vp, _sz, C.c_int]),
     "ofb_ctx_launch_count": (C.c_int, [_vp, C.POINTER(C.c_ulonglong)]),
     "ofb_ctx_profile_enable": (C.c_int, [_vp, C.c_int]),
     "ofb_ctx_profile_read": (C.c_int, [_vp, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_ulonglong)]),

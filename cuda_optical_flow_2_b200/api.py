@@ -94,6 +94,18 @@ class Context:
     def solve(self, mode: int) -> None:
         L.check(self._lib.ofb_ctx_set_solve(self._h, int(mode)))
 
+    @property
+    def host_threads(self) -> int:
+        """Host threads that extract channel 0 of 3-channel host images in `flow_pairs_host` (0: the device does it
+        after uploading all three channels)."""
+        v = C.c_int(0)
+        L.check(self._lib.ofb_ctx_get_host_threads(self._h, C.byref(v)))
+        return v.value
+
+    @host_threads.setter
+    def host_threads(self, n: int) -> None:
+        L.check(self._lib.ofb_ctx_set_host_threads(self._h, int(n)))
+
     def reserve_pairs(self, w: int, h: int, levels: int, win: int, n_pairs: int) -> None:
         """Size the context workspace for flow_pairs_device calls of this shape now (a later growth would invalidate
         CUDA graphs captured from earlier calls)."""

@@ -1,4 +1,5 @@
 // ofb_api.cu -- context object and the extern "C" surface declared in include/ofb200.h.
+#include "host_extract.hpp"
 #include "ofb_common.cuh"
 
 #include <cstdarg>
@@ -52,6 +53,13 @@ struct ofb_ctx {
         cudaEvent_t a, b;
     };
     double *bil_lut = nullptr; // range-weight table of the bilateral pre-filter (device)
+    // 3-channel host images: channel 0 extracted by host threads into pinned planar staging buffers, one pair of buffers
+    // per lane (ofb_ctx_set_host_threads; 0 = all three channels are uploaded and the device drops two)
+    int host_threads = 0;
+    ofb::HostPool *pool = nullptr;
+    uint8_t *stage = nullptr;
+    size_t stage_bytes = 0;
+    cudaEvent_t stage_ev[OFB_LANES] = {};
     bool prof_on = false;
     std::vector<ProfRec> prof;
 };
@@ -369,6 +377,10 @@ int ofb_ctx_create(int device, ofb_ctx **out)
         if (v >= 1 && v <= OFB_LANES) c->lanes = v;
     }
     if (const char *e = getenv("OFB_E2E_SUB")) c->sub_pairs = atoi(e) > 0 ? atoi(e) : 0;
+    if (const char *e = getenv("OFB_HOST_THREADS")) {
+        const int v = atoi(e);
+        if (v >= 0 && v <= 64) c->host_threads = v;
+    }
     e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) {
         set_error("cudaStreamCreate failed: %s", cudaGetErrorString(e));
@@ -409,11 +421,56 @@ int ofb_ctx_destroy(ofb_ctx *c)
             if (c->bil_lut) cudaFree(c->bil_lut);
             if (c->ws_event) cudaEventDestroy(c->ws_event);
             if (c->stream) cudaStreamDestroy(c->stream);
-            for (int l = 0; l < OFB_LANES; l++)
+            for (int l = 0; l < OFB_LANES; l++) {
                 if (c->lane_stream[l]) cudaStreamDestroy(c->lane_stream[l]);
+                if (c->stage_ev[l]) cudaEventDestroy(c->stage_ev[l]);
+            }
+            if (c->stage) cudaFreeHost(c->stage);
         }
     }
+    delete c->pool;
     delete c;
+    return OFB_OK;
+}
+
+int ofb_ctx_set_host_threads(ofb_ctx *c, int threads)
+{
+    OFB_CHECK_CTX(c);
+    if (threads < 0 || threads > 64) {
+        set_error("host threads %d outside 0..64", threads);
+        return OFB_ERR_INVALID;
+    }
+    if (c->pool && c->pool->threads() != threads) {
+        delete c->pool;
+        c->pool = nullptr;
+    }
+    c->host_threads = threads;
+    return OFB_OK;
+}
+
+int ofb_ctx_get_host_threads(const ofb_ctx *c, int *threads)
+{
+    OFB_CHECK_CTX(c);
+    if (threads) *threads = c->host_threads;
+    return OFB_OK;
+}
+
+int ofb_c3_extract_host(const unsigned char *src_c3, unsigned char *dst_planar, size_t n_pixels, int threads)
+{
+    if (!src_c3 || !dst_planar || threads < 1 || threads > 64) {
+        set_error("c3_extract_host: bad arguments");
+        return OFB_ERR_INVALID;
+    }
+    try {
+        ofb::HostPool pool(threads);
+        // (the two-set helper with one set: the second set is empty)
+        const size_t half = n_pixels / 2;
+        ofb::c3_extract_pair_sets(&pool, src_c3, src_c3 + 3 * half, dst_planar, dst_planar + half, half);
+        ofb::c3_extract_channel0(src_c3 + 3 * 2 * half, dst_planar + 2 * half, n_pixels - 2 * half);
+    } catch (...) {
+        set_error("c3_extract_host: could not start the host threads");
+        return OFB_ERR_NOMEM;
+    }
     return OFB_OK;
 }
 
@@ -953,6 +1010,30 @@ static int flow_pairs_host_impl(ofb_ctx *c, const ofb_params *p, const unsigned 
     }
     rc = ws_reserve(c, lane_bytes * LANES);
     if (rc) return rc;
+    // 3-channel input with host threads: channel 0 is extracted on the host into pinned planar staging buffers (one
+    // prev + one next buffer per lane) and only those bytes are uploaded (host_extract.cpp)
+    const bool host_extract = channels == 3 && c->host_threads > 0;
+    const size_t frame_px = (size_t)p->w * p->h, stage_lane = 2 * frame_px * sub;
+    bool stage_used[OFB_LANES] = {};
+    if (host_extract) {
+        if (!c->pool) {
+            try {
+                c->pool = new ofb::HostPool(c->host_threads);
+            } catch (...) {
+                set_error("flow_pairs_host: could not start %d host threads", c->host_threads);
+                return OFB_ERR_NOMEM;
+            }
+        }
+        if (c->stage_bytes < stage_lane * LANES) {
+            if (c->stage) OFB_CUDA_TRY(cudaFreeHost(c->stage));
+            c->stage = nullptr;
+            c->stage_bytes = 0;
+            OFB_CUDA_TRY(cudaHostAlloc(reinterpret_cast<void **>(&c->stage), stage_lane * LANES, cudaHostAllocDefault));
+            c->stage_bytes = stage_lane * LANES;
+        }
+        for (int lane = 0; lane < LANES; lane++)
+            if (!c->stage_ev[lane]) OFB_CUDA_TRY(cudaEventCreateWithFlags(&c->stage_ev[lane], cudaEventDisableTiming));
+    }
     for (int lane = 0; lane < LANES; lane++)
         if ((rc = ws_acquire(c, c->lane_stream[lane]))) return rc;
     for (int first = 0, sb = 0; first < n; first += sub, sb++) {
@@ -967,6 +1048,16 @@ static int flow_pairs_host_impl(ofb_ctx *c, const ofb_params *p, const unsigned 
                                            (size_t)p->h * cnt, cudaMemcpyHostToDevice, st));
             OFB_CUDA_TRY(cudaMemcpy2DAsync(B + off_n0, pitch0, next_h + (size_t)first * p->w * p->h, (size_t)p->w, (size_t)p->w,
                                            (size_t)p->h * cnt, cudaMemcpyHostToDevice, st));
+        } else if (host_extract) {
+            uint8_t *sp = c->stage + stage_lane * lane, *sn = sp + frame_px * sub;
+            if (stage_used[lane]) OFB_CUDA_TRY(cudaEventSynchronize(c->stage_ev[lane])); // the lane's previous upload has left the buffers
+            ofb::c3_extract_pair_sets(c->pool, prev_h + c3 * first, next_h + c3 * first, sp, sn, frame_px * cnt);
+            OFB_CUDA_TRY(cudaMemcpy2DAsync(B + off_p0, pitch0, sp, (size_t)p->w, (size_t)p->w, (size_t)p->h * cnt,
+                                           cudaMemcpyHostToDevice, st));
+            OFB_CUDA_TRY(cudaMemcpy2DAsync(B + off_n0, pitch0, sn, (size_t)p->w, (size_t)p->w, (size_t)p->h * cnt,
+                                           cudaMemcpyHostToDevice, st));
+            OFB_CUDA_TRY(cudaEventRecord(c->stage_ev[lane], st));
+            stage_used[lane] = true;
         } else {
             OFB_CUDA_TRY(cudaMemcpyAsync(B + off_c3, prev_h + c3 * first, c3 * cnt, cudaMemcpyHostToDevice, st));
             OFB_CUDA_TRY(cudaMemcpyAsync(B + off_c3 + c3 * sub, next_h + c3 * first, c3 * cnt, cudaMemcpyHostToDevice, st));

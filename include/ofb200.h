@@ -81,6 +81,17 @@ int ofb_ctx_reserve_pairs(ofb_ctx *ctx, const ofb_params *p); /* workspace for o
 /* Solve mode (OFB_SOLVE_*) of every fused-LK launch made through this context from now on. */
 int ofb_ctx_set_solve(ofb_ctx *ctx, int solve_mode);
 int ofb_ctx_get_solve(const ofb_ctx *ctx, int *solve_mode);
+/* Host threads of the batched host entry points (ofb_flow_pairs_host / _ex) for 3-channel input, 0..64, default 0 (or
+ * OFB_HOST_THREADS in the environment).  The reference's host images are 3-channel and its kernels read channel 0
+ * (OptFlowGpu.cu:1040-1090).  With 0 all three channels are uploaded and the device drops two; with n > 0 a pool of n
+ * host threads (the caller's included) extracts channel 0 into pinned staging buffers while earlier sub-batches are in
+ * flight and a third of the bytes cross PCIe -- the results are identical.  The end-to-end path is bound by PCIe bytes,
+ * so this is what bench.py's `e2e` record runs with. */
+int ofb_ctx_set_host_threads(ofb_ctx *ctx, int threads);
+int ofb_ctx_get_host_threads(const ofb_ctx *ctx, int *threads);
+/* The extraction itself (host only, no device involved): dst_planar[i] = src_c3[3 * i], i < n_pixels, on `threads`
+ * host threads (1..64). */
+int ofb_c3_extract_host(const unsigned char *src_c3, unsigned char *dst_planar, size_t n_pixels, int threads);
 
 /* ------------------------------------------------------------------------------------------
  * Device-resident hot path (what the metric is quoted on).  Asynchronous on `stream`

@@ -31,6 +31,25 @@ def test_library_exports_every_declared_symbol():
     assert lib.ofb_version() == 100
 
 
+@pytest.mark.parametrize("npix,threads", [(0, 1), (1, 1), (15, 2), (16, 1), (1000003, 3), (2 * 1920 * 1080, 4)])
+def test_c3_extract_host(npix, threads):
+    """Host-side extraction of channel 0 (what the batched host entry point does with ofb_ctx_set_host_threads): pure
+    host code, no device involved."""
+    import numpy as np
+    from cuda_optical_flow_2_b200 import _lib
+
+    lib = _lib.load()
+    rng = np.random.default_rng(npix + threads)
+    src = rng.integers(0, 256, size=(npix, 3), dtype=np.uint8)
+    dst = np.full(npix + 32, 0xAB, np.uint8)  # guard bytes behind the output
+    rc = lib.ofb_c3_extract_host(src.ctypes.data_as(C.c_void_p), dst.ctypes.data_as(C.c_void_p), npix, threads)
+    assert rc == 0, lib.ofb_last_error()
+    assert np.array_equal(dst[:npix], src[:, 0])
+    assert (dst[npix:] == 0xAB).all()
+    assert lib.ofb_c3_extract_host(None, dst.ctypes.data_as(C.c_void_p), npix, threads) != 0
+    assert lib.ofb_c3_extract_host(src.ctypes.data_as(C.c_void_p), dst.ctypes.data_as(C.c_void_p), npix, 0) != 0
+
+
 def test_header_compiles_as_c():
     """The boundary is plain C: no C++ or torch types in the signatures."""
     r = subprocess.run(["gcc", "-std=c99", "-fsyntax-only", "-x", "c", HEADER], capture_output=True, text=True)

@@ -497,3 +497,30 @@ def test_flow_pairs_host_c3_layout_any_width(ctx, oracle, w, h):
         for k in range(levels):
             assert_flow_identical(got[k][i], ref[k], f"{w}x{h} pair {i} level {k}")
         assert_flow_identical(total[i], cums[0], f"{w}x{h} pair {i} total flow")
+
+
+@pytest.mark.parametrize("threads,n,w,h", [(1, 5, 130, 66), (4, 20, 322, 246), (3, 26, 64, 48)])
+def test_flow_pairs_host_c3_host_threads(ctx, oracle, threads, n, w, h):
+    """3-channel host images with channel 0 extracted by host threads into pinned staging buffers (ofb_ctx_set_host_threads):
+    identical to the planar call, channels 1 and 2 are never looked at, and the staging buffers of a lane are reused
+    across many sub-batches."""
+    levels, win = 2, 5
+    rng = np.random.default_rng(n)
+    prevs = np.stack([oracle.make_frame(w, h, 0, 0, 4, 500 + i) for i in range(n)])
+    nexts = np.stack([oracle.make_frame(w, h, 0.5, -0.25 * (i % 3), 4, 500 + i) for i in range(n)])
+    p3 = rng.integers(0, 256, size=(n, h, w, 3), dtype=np.uint8)
+    n3 = rng.integers(0, 256, size=(n, h, w, 3), dtype=np.uint8)
+    p3[..., 0], n3[..., 0] = prevs, nexts
+    ref = ctx.flow_pairs_host(prevs, nexts, levels, win)
+    assert ctx.host_threads == 0
+    dev = ctx.flow_pairs_host(p3, n3, levels, win)
+    ctx.host_threads = threads
+    try:
+        assert ctx.host_threads == threads
+        for rep in range(2):  # (second call: pool and staging buffers already exist)
+            got = ctx.flow_pairs_host(p3, n3, levels, win)
+            for k in range(levels):
+                assert np.array_equal(got[k].view(np.uint32), ref[k].view(np.uint32)), f"level {k} rep {rep}"
+                assert np.array_equal(dev[k].view(np.uint32), ref[k].view(np.uint32)), f"level {k} device extraction"
+    finally:
+        ctx.host_threads = 0
