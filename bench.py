@@ -555,6 +555,8 @@ def e2e_block(env, ctx, args):
     if d2h_both:
         full["frac_of_box_d2h_ceiling"] = full["d2h_gbs_all_ranks"] / d2h_both
         lean["frac_of_box_d2h_ceiling"] = lean["d2h_gbs_all_ranks"] / d2h_both
+        # both directions at once: what the box moves when every rank copies in and out concurrently
+        full["frac_of_box_both_directions_ceiling"] = full["pcie_gbs_both_directions_all_ranks"] / (d2h_both + h2d_both)
     full["lean"] = lean
     full["box_ceiling_gbs"] = ceiling
     return full

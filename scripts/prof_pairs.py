@@ -24,6 +24,7 @@ for _ in range(reps):
 torch.cuda.synchronize()
 dt = (time.perf_counter() - t0) / reps
 print(f"{pairs} pairs {w}x{h} L{levels} win{win} mode{mode} solve{ctx.solve}: {dt*1e3:.3f} ms/step, {w*h/1e6*pairs/dt:.0f} Mpx-pairs/s")
+import signal; signal.signal(signal.SIGPIPE, signal.SIG_DFL)
 for k in range(levels):
     ms, n = ctx.profile_read(k)
     npx = (w >> k) * (h >> k) * pairs
