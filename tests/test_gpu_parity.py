@@ -334,6 +334,42 @@ def test_config3_batch_equals_single_pairs(ctx, oracle):
         assert_flow_identical(batch[k][5].cpu().numpy(), ref[k], f"batch pair 5 level {k}")
 
 
+@pytest.mark.parametrize("solve", [0, 1])
+def test_config3_one_ranks_share_of_the_full_batch(ctx, oracle, solve):
+    """configs[3] at the size one of eight B200 gets (512 of the 4096 pairs of 1080p, the bench's per-launch class): the
+    batch is 4 distinct pairs tiled, and every copy must be bit-identical to the first one of its kind in every level --
+    a property that does not need the oracle at full size -- while pair 1 is checked against the oracle itself (exact
+    solve) or against the tolerance (fast solve)."""
+    torch = _torch()
+    from cuda_optical_flow_2_b200 import planar_to_device
+
+    w, h, levels, win, distinct, n = 1920, 1080, 3, 9, 4, 512
+    prevs = np.stack([oracle.make_frame(w, h, 0, 0, 8, 60 + i) for i in range(distinct)])
+    nexts = np.stack([oracle.make_frame(w, h, 0.5 + i, 1.5 - i, 8, 60 + i) for i in range(distinct)])
+    dp = planar_to_device(prevs).repeat(n // distinct, 1, 1)
+    dn = planar_to_device(nexts).repeat(n // distinct, 1, 1)
+    old = ctx.solve
+    ctx.solve = solve
+    try:
+        flows = ctx.flow_pairs_device(dp, dn, w, levels, win)
+        torch.cuda.synchronize()
+    finally:
+        ctx.solve = old
+    for k in range(levels):
+        f = flows[k].view(torch.int32).view(n // distinct, distinct, -1)
+        assert bool((f == f[0:1]).all()), f"level {k}: copies of the same pair differ inside one batch"
+    ref = oracle.flow_pair(prevs[1], nexts[1], levels, win, 2, oracle.SUMS_EXACT)
+    if solve == 0:
+        for k in range(levels):
+            assert_flow_identical(flows[k][n - distinct + 1].cpu().numpy(), ref[k], f"last copy of pair 1, level {k}")
+    else:
+        got = flows[levels - 1][n - distinct + 1].cpu().numpy()
+        fin = np.isfinite(ref[levels - 1])
+        assert np.array_equal(np.isfinite(got), fin)
+        d = np.abs(got[fin] - ref[levels - 1][fin])
+        assert (d <= TOL_ABS + TOL_REL * np.abs(ref[levels - 1][fin])).all()
+
+
 def test_config4_8k_whole_frame_vs_oracle(ctx, oracle):
     """configs[4] frame (7680x4320, 4 levels, window 9) on one GPU against the oracle; the row-strip
     split of the same frame is checked against this whole-frame result in tests/test_dist.py."""
