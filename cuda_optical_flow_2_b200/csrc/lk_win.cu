@@ -3,6 +3,7 @@
 #include "lk_level.cuh"
 
 #include <algorithm>
+#include <climits>
 #include <cstdlib>
 
 #ifndef LK_WIN
@@ -84,6 +85,24 @@ static int launch_one(const LkLevelArgs &a, cudaStream_t stream, unsigned long l
         if (v > 0) rows_per_block = v < out_rows ? v : out_rows;
     }
     const int nby = (out_rows + rows_per_block - 1) / rows_per_block;
+    // A big batch of full-height CTAs drains for a whole CTA lifetime while the SMs run emptier and emptier (one 1080p
+    // column strip lives ~0.3 ms, 3 % of a 1024-pair launch).  The last wave's worth of pairs is therefore cut into 4 row
+    // blocks each: a quarter of the drain for 11 halo rows more per block on those pairs only.
+    int tail_pair0 = INT_MAX, tail_shift = 0, tail_rows = 0, grid_z = a.n_pairs;
+    {
+        const char *env = getenv("OFB_LK_TAIL"); // developer override: 0 = off, n = 2^n row blocks per tail pair
+        const char *envw = getenv("OFB_LK_TAIL_WAVES"); // ... and the length of the tail in tenths of a wave
+        const int shift = env ? atoi(env) : 2;
+        const int slots = n_sm * C::MIN_BLOCKS;
+        const int tail_pairs = ((slots + strips - 1) / strips * (envw ? atoi(envw) : 10) + 9) / 10;
+        if (shift > 0 && shift <= 4 && nby == 1 && a.npush == 0 && a.nwait == 0 && out_rows >= (2 * C::CH << shift) &&
+            tail_pairs > 0 && (long long)a.n_pairs * strips >= 4ll * slots && tail_pairs < a.n_pairs) {
+            tail_shift = shift;
+            tail_pair0 = a.n_pairs - tail_pairs;
+            tail_rows = (out_rows + (1 << shift) - 1) >> shift;
+            grid_z = tail_pair0 + (tail_pairs << tail_shift);
+        }
+    }
 
     LkKernelParams p;
     p.next = a.next;
@@ -96,6 +115,9 @@ static int launch_one(const LkLevelArgs &a, cudaStream_t stream, unsigned long l
     p.out_y0 = a.out_y0;
     p.out_y1 = a.out_y1;
     p.rows_per_block = rows_per_block;
+    p.tail_pair0 = tail_pair0;
+    p.tail_shift = tail_shift;
+    p.tail_rows = tail_rows;
     p.as_written = (a.warp_mode == OFB_WARP_AS_WRITTEN) ? 1 : 0;
     p.scale2 = 2.0f * a.flow_scale;
     p.scale512 = 512.0f * a.flow_scale;
@@ -138,7 +160,7 @@ static int launch_one(const LkLevelArgs &a, cudaStream_t stream, unsigned long l
         if (d < a.nwait) p.wait[d] = LkPeerWait{a.wait[d].flag, a.wait[d].crow_lo, a.wait[d].crow_hi};
     }
 
-    dim3 grid((unsigned)strips, (unsigned)nby, (unsigned)a.n_pairs);
+    dim3 grid((unsigned)strips, (unsigned)nby, (unsigned)grid_z);
     OFB_CUDA_TRY(launch_pdl(lk_level_kernel<WIN, MODE, CUMOUT, FAST, PEER, COMP>, grid, dim3(LK_NT), C::smem_bytes(FAST, CUMOUT && MODE != 0),
                             stream, tmP, tmQ, tmC, tmC2, p));
     if (launches) ++*launches;

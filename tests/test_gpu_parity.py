@@ -334,6 +334,33 @@ def test_config3_batch_equals_single_pairs(ctx, oracle):
         assert_flow_identical(batch[k][5].cpu().numpy(), ref[k], f"batch pair 5 level {k}")
 
 
+@pytest.mark.parametrize("mode", [0, 1, 2])
+def test_big_batch_short_ctas_at_the_tail(ctx, oracle, mode, monkeypatch):
+    """A batch of many pairs ends with a wave of short CTAs (csrc/lk_win.cu: the last pairs are cut into 4 row blocks so
+    that the launch drains faster).  Small frames, 800 pairs: every copy of a pair -- in the full-height part and in the
+    tail -- is bit-identical, equals the oracle, and equals the launch with the tail switched off."""
+    torch = _torch()
+    from cuda_optical_flow_2_b200 import planar_to_device
+
+    w, h, levels, win, distinct, n = 248, 136, 2, 9, 4, 800
+    prevs = np.stack([oracle.make_frame(w, h, 0, 0, 4, 70 + i) for i in range(distinct)])
+    nexts = np.stack([oracle.make_frame(w, h, 0.7 + i, 1.0 - i, 4, 70 + i) for i in range(distinct)])
+    dp = planar_to_device(prevs).repeat(n // distinct, 1, 1)
+    dn = planar_to_device(nexts).repeat(n // distinct, 1, 1)
+    flows = [f.clone() for f in ctx.flow_pairs_device(dp, dn, w, levels, win, warp_mode=mode)]
+    monkeypatch.setenv("OFB_LK_TAIL", "0")
+    plain = ctx.flow_pairs_device(dp, dn, w, levels, win, warp_mode=mode)
+    torch.cuda.synchronize()
+    for k in range(levels):
+        f = flows[k].view(torch.int32).view(n // distinct, distinct, -1)
+        assert bool((f == f[0:1]).all()), f"level {k}: copies of the same pair differ inside one batch"
+        assert bool((flows[k].view(torch.int32) == plain[k].view(torch.int32)).all()), f"level {k}: tail on / off differ"
+    for i in range(distinct):
+        ref = oracle.flow_pair(prevs[i], nexts[i], levels, win, mode, oracle.SUMS_EXACT)
+        for k in range(levels):
+            assert_flow_identical(flows[k][n - distinct + i].cpu().numpy(), ref[k], f"pair {i} (tail copy), level {k}")
+
+
 @pytest.mark.parametrize("solve", [0, 1])
 def test_config3_one_ranks_share_of_the_full_batch(ctx, oracle, solve):
     """configs[3] at the size one of eight B200 gets (512 of the 4096 pairs of 1080p, the bench's per-launch class): the
