@@ -170,6 +170,30 @@ def test_flow_pairs_device_identical_to_oracle(ctx, oracle, mode, w, h, levels, 
         assert_flow_identical(total[i].cpu().numpy(), cums[0], f"pair {i} total flow")
 
 
+@pytest.mark.parametrize("mode", [0, 1, 2])
+@pytest.mark.parametrize("win", [3, 7, 11, 13, 15, 17, 19])
+@pytest.mark.parametrize("w,h,want_total", [(256, 160, False), (256, 160, True), (262, 150, False)])
+def test_every_window_on_warped_levels_identical_to_oracle(ctx, oracle, mode, win, w, h, want_total):
+    """The window sizes the other multi-level tests leave out, three levels, every warp mode: even sizes without the total
+    flow (level 0 composes the coarser cumulative flow on the fly), with it (level 0 writes it), and a size whose coarser
+    widths are odd (no tensor map for the coarser flow, clamped coarse indices)."""
+    torch = _torch()
+    from cuda_optical_flow_2_b200 import planar_to_device
+
+    levels = 3
+    prev = oracle.make_frame(w, h, 0, 0, 6, 900 + win)
+    nxt = oracle.make_frame(w, h, 1.75, -2.5, 6, 900 + win)
+    total = torch.empty((1, h, w, 2), dtype=torch.float32, device="cuda") if want_total else None
+    flows = ctx.flow_pairs_device(planar_to_device(prev[None]), planar_to_device(nxt[None]), w, levels, win, warp_mode=mode,
+                                  total_flow=total)
+    torch.cuda.synchronize()
+    ref, cums = oracle.flow_pair(prev, nxt, levels, win, mode, oracle.SUMS_EXACT, 1.0, want_cum=True)
+    for k in range(levels - 1, -1, -1):
+        assert_flow_identical(flows[k][0].cpu().numpy(), ref[k], f"win {win} level {k} mode {mode}")
+    if want_total:
+        assert_flow_identical(total[0].cpu().numpy(), cums[0], f"win {win} total flow")
+
+
 @pytest.mark.parametrize("case", ["far_shift", "split_motion", "coarse_outliers"])
 def test_staged_window_and_fallbacks_identical_to_oracle(ctx, oracle, case):
     """The warped levels gather from a window of `next` staged around the tile, displaced by the local coarser
