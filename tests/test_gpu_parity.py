@@ -521,7 +521,8 @@ def test_fast_solve_flat_areas_same_nonfinite_pixels(fast_ctx, oracle):
 
 
 @pytest.mark.parametrize("mode", [0, 1, 2])
-@pytest.mark.parametrize("w,h,levels,win", [(640, 480, 4, 9), (322, 246, 3, 5), (1920, 1080, 3, 9), (400, 300, 3, 15)])
+@pytest.mark.parametrize("w,h,levels,win", [(640, 480, 4, 9), (322, 246, 3, 5), (1920, 1080, 3, 9), (400, 300, 3, 15), (256, 160, 3, 3),
+                                            (256, 160, 3, 7), (262, 150, 3, 11), (256, 160, 3, 13), (256, 160, 3, 17), (262, 150, 3, 19)])
 def test_fast_solve_every_level_on_identical_inputs(ctx, oracle, mode, w, h, levels, win):
     """Per level, on the EXACT pipeline's inputs (pyramid level + coarser cumulative flow): the tolerance-mode
     kernel against the oracle's residual flow and cumulative flow of that level."""
